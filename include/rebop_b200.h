@@ -1,0 +1,176 @@
+/*
+ * rebop_b200.h -- C ABI of the B200-native Gillespie (direct method) ensemble engine.
+ *
+ * This is the drop-in boundary for rebop's hot path.  The reference
+ * (Armavica/rebop v0.9.7) has no FFI for this path: it is one Rust crate whose
+ * only ABI is the pyo3 module.  Each entry point below therefore cites the Rust
+ * item it stands in for (paths relative to the reference tree); a Rust `-sys`
+ * crate, the pyo3 module or any other host binds exactly these symbols
+ * (INTEGRATION.md shows the bindings).
+ *
+ * Conventions
+ *   - Every function returns a rebop_status (0 = ok).  On failure a thread-local
+ *     message is available from rebop_b200_last_error().
+ *   - Handles are opaque, created/destroyed by the library, and not internally
+ *     synchronised (one thread per handle, like `&mut self`).
+ *   - Caller-owned input arrays are copied before the call returns.
+ *   - There is no CPU fallback: without a CUDA device every compute entry fails
+ *     with REBOP_ERR_CUDA.
+ *   - Species counts are carried as int32 on the device (the reference uses
+ *     isize); inputs outside the int32 range are rejected.
+ */
+#ifndef REBOP_B200_H
+#define REBOP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  REBOP_OK = 0,
+  REBOP_ERR_INVALID = 1,       /* bad argument / shape (the reference's assert! panics, src/gillespie.rs:227-237) */
+  REBOP_ERR_OUT_OF_RANGE = 2,  /* species index out of range (src/gillespie.rs:229-233, test issue85_oob) */
+  REBOP_ERR_PARSE = 3,         /* "Rate expression not understood" (src/pyo3_gillespie.rs:95-98) */
+  REBOP_ERR_MISSING_PARAM = 4, /* "Parameter {s} should have a value" (src/expr.rs:70-72) */
+  REBOP_ERR_CUDA = 5,          /* CUDA runtime error, or no device */
+  REBOP_ERR_NVRTC = 6,         /* run-time specialisation failed; message holds the compile log */
+  REBOP_ERR_LIMIT = 7,         /* network too large for the selected kernel */
+  REBOP_ERR_ITER_CAP = 8       /* a trajectory hit the per-launch iteration cap (state is kept; call again) */
+} rebop_status;
+
+/* Arithmetic flavour: which of the reference's two engines is reproduced bit for bit. */
+typedef enum {
+  REBOP_ARITH_API = 0,   /* src/gillespie.rs: factor-by-factor f64 LMA product, select = count(cum < chosen) */
+  REBOP_ARITH_MACRO = 1  /* src/gillespie_macro.rs: integer falling factorial, first-match select */
+} rebop_arith;
+
+/* Which kernel advances the ensemble. */
+typedef enum {
+  REBOP_KERNEL_AUTO = 0,   /* NVRTC-specialised when possible, else table-driven */
+  REBOP_KERNEL_TABLE = 1,  /* K1: generic kernel, network tables in __constant__ memory */
+  REBOP_KERNEL_NVRTC = 2   /* K2: network-specialised source compiled at run time */
+} rebop_kernel_kind;
+
+/* Expression byte-code = post-order walk of `Expr` (src/expr.rs:9-21). */
+typedef enum {
+  REBOP_OP_CONST = 0, REBOP_OP_SPECIES = 1, REBOP_OP_NEG = 2, REBOP_OP_ADD = 3, REBOP_OP_SUB = 4,
+  REBOP_OP_MUL = 5, REBOP_OP_DIV = 6, REBOP_OP_POW = 7, REBOP_OP_MAX = 8, REBOP_OP_MIN = 9,
+  REBOP_OP_EXP = 10
+} rebop_opcode;
+
+typedef struct {
+  int32_t op;    /* rebop_opcode */
+  int32_t index; /* species index for REBOP_OP_SPECIES */
+  double value;  /* constant for REBOP_OP_CONST */
+} rebop_expr_op;
+
+typedef struct rebop_network rebop_network;
+typedef struct rebop_batch rebop_batch;
+typedef struct rebop_pexpr rebop_pexpr;
+
+const char* rebop_b200_last_error(void);
+const char* rebop_b200_version(void);
+/* Number of CUDA devices visible (0 without a driver); never fails. */
+int rebop_b200_device_count(void);
+
+/* ---- network: gillespie::Gillespie::{new, add_reaction}, Rate::{lma, lma_sparse, expr} ---- */
+
+/* Gillespie::new (src/gillespie.rs:168-176): a network over n_species species. */
+int rebop_network_create(uint32_t n_species, int arith, rebop_network** out);
+void rebop_network_destroy(rebop_network* net);
+/* add_reaction(Rate::lma(k, exponents), differences) (src/gillespie.rs:24-26,225-244).
+ * exponents, differences: [n_species]. */
+int rebop_network_add_reaction_lma(rebop_network* net, double k, const uint32_t* exponents,
+                                   const int64_t* differences);
+/* add_reaction(Rate::lma_sparse(k, [(index, exponent)...]), differences) (src/gillespie.rs:29-31).
+ * Terms are multiplied in the order given, as the reference does. */
+int rebop_network_add_reaction_lma_sparse(rebop_network* net, double k, const uint32_t* index,
+                                          const uint32_t* exponent, size_t n_terms,
+                                          const int64_t* differences);
+/* add_reaction(Rate::expr(e), differences) (src/gillespie.rs:33-35). */
+int rebop_network_add_reaction_expr(rebop_network* net, const rebop_expr_op* program, size_t n_ops,
+                                    const int64_t* differences);
+int rebop_network_nb_species(const rebop_network* net, uint32_t* out);   /* src/gillespie.rs:200 */
+int rebop_network_nb_reactions(const rebop_network* net, uint32_t* out); /* src/gillespie.rs:210 */
+
+/* Source text of the network-specialised kernel (K2) the engine would compile for this network,
+ * and the sm_100a cubin NVRTC produces from it.  Neither needs a GPU.  *needed receives the size
+ * in bytes (the source includes its NUL terminator). */
+int rebop_network_codegen(const rebop_network* net, char* buf, size_t cap, size_t* needed);
+int rebop_network_jit_cubin(const rebop_network* net, char* buf, size_t cap, size_t* needed);
+
+/* ---- rate expressions: the `PExpr` front end (src/expr.rs:43-273) ---- */
+
+/* "...".parse::<PExpr>() (src/expr.rs:134-141). REBOP_ERR_PARSE on failure. */
+int rebop_pexpr_parse(const char* text, rebop_pexpr** out);
+void rebop_pexpr_destroy(rebop_pexpr* e);
+/* Display for PExpr (src/expr.rs:112-128). Writes a NUL-terminated string; *needed (optional)
+ * receives the length including the terminator. */
+int rebop_pexpr_format(const rebop_pexpr* e, char* buf, size_t cap, size_t* needed);
+/* PExpr::to_expr (src/expr.rs:58-109): species names resolve first, then parameters;
+ * REBOP_ERR_MISSING_PARAM ("Parameter {s} should have a value") otherwise.
+ * Emits the post-order program; *n_ops receives its length (call with cap = 0 to size it). */
+int rebop_pexpr_lower(const rebop_pexpr* e, const char* const* species_names, size_t n_species,
+                      const char* const* param_names, const double* param_values, size_t n_params,
+                      rebop_expr_op* program, size_t cap, size_t* n_ops);
+
+/* ---- ensemble of trajectories ---- */
+
+/* N instances of Gillespie::new_with_seed(x0, _, seed_n) (src/gillespie.rs:179-187) on `device`.
+ * x0: [n_species] when x0_per_trajectory == 0, else [n_traj][n_species].
+ * seeds: [n_traj], or NULL for seed_n = seed_base + n. */
+int rebop_batch_create(const rebop_network* net, int device, size_t n_traj, const int64_t* x0,
+                       int x0_per_trajectory, const uint64_t* seeds, uint64_t seed_base,
+                       rebop_batch** out);
+void rebop_batch_destroy(rebop_batch* b);
+int rebop_batch_set_kernel(rebop_batch* b, int kind);                 /* rebop_kernel_kind */
+int rebop_batch_get_kernel(const rebop_batch* b, int* kind);          /* the kernel the last launch used */
+int rebop_batch_set_max_iters(rebop_batch* b, uint32_t max_iters);    /* watchdog per launch; 0 = 2^32-1 */
+/* Gillespie::seed (src/gillespie.rs:189-191) for every trajectory. */
+int rebop_batch_seed(rebop_batch* b, const uint64_t* seeds, uint64_t seed_base);
+/* get/set_time, get/set_species (src/gillespie.rs:246-267). species: [n_traj][n_species]. */
+int rebop_batch_get_time(rebop_batch* b, double* t);
+int rebop_batch_set_time(rebop_batch* b, double t);
+int rebop_batch_get_species(rebop_batch* b, int64_t* species);
+int rebop_batch_set_species(rebop_batch* b, const int64_t* species, int per_trajectory);
+/* Gillespie::advance_until (src/gillespie.rs:315-344) on every trajectory. */
+int rebop_batch_advance_until(rebop_batch* b, double tmax);
+/* The pyo3 grid loop (src/pyo3_gillespie.rs:197-208): for i in 0..=nb_steps
+ * { advance_until(tmax*i/nb_steps); record species[save_idx] }.  save_idx NULL = all species.
+ * Samples stay on the device as int32 [nb_steps+1][n_save][ld] (ld >= n_traj).
+ * host_out (optional): caller buffer of (nb_steps+1)*n_save*n_traj int32 that receives them
+ * densely as [step][save][trajectory]. */
+int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
+                         uint32_t n_save, int32_t* host_out);
+/* Device view of the last run_grid's samples. */
+int rebop_batch_samples_device(const rebop_batch* b, const int32_t** dev_ptr, size_t* ld,
+                               uint32_t* n_rows);
+/* Copy the last run_grid's samples to the host: int32 or int64, [step][save][trajectory]. */
+int rebop_batch_samples_host_i32(rebop_batch* b, int32_t* out);
+int rebop_batch_samples_host_i64(rebop_batch* b, int64_t* out);
+/* K4: per (step, saved species) sum and sum of squares over the trajectories of this batch,
+ * as exact integers (so that sums over GPUs are order-independent). sum, sumsq: [n_rows]. */
+int rebop_batch_sample_sums(rebop_batch* b, int64_t* sum, uint64_t* sumsq);
+/* Same, left on the device for a following all-reduce: int64 [2][n_rows] (sums, then squares). */
+int rebop_batch_sample_sums_device(rebop_batch* b, const int64_t** dev_ptr, uint32_t* n_rows);
+/* Applied reactions since creation, and during the last launch. */
+int rebop_batch_events(rebop_batch* b, uint64_t* total, uint64_t* last_launch);
+/* Device time of the last advance_until / run_grid launch in milliseconds (CUDA events). */
+int rebop_batch_last_kernel_ms(rebop_batch* b, float* ms);
+int rebop_batch_size(const rebop_batch* b, size_t* n_traj);
+/* Block until the device has finished the batch's queued work. */
+int rebop_batch_synchronize(rebop_batch* b);
+
+/* ---- measurement helpers ---- */
+
+/* Sustained non-fused FP64 issue rate of `device` in operations per second (independent
+ * DADD/DMUL chains, all SMs) -- the denominator of the per-event FP64 roofline. */
+int rebop_b200_measure_fp64_rate(int device, double* ops_per_second, double* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REBOP_B200_H */

@@ -1,0 +1,5 @@
+"""rebop_b200 -- B200-native ensemble engine for rebop's Gillespie direct method."""
+from rebop_b200 import _ffi  # noqa: F401  (fails loudly when the CUDA library is not built)
+
+__version__ = _ffi.lib.rebop_b200_version().decode()
+__all__ = ("__version__",)

@@ -1,0 +1,363 @@
+"""ctypes binding of the C ABI declared in include/rebop_b200.h.
+
+This is the Python-side equivalent of the Rust `-sys` crate: thin, one function per
+exported symbol, no logic.  The library is built in-tree (`rebop_b200/librebop_b200.so`);
+if it is missing the import fails loudly -- there is no CPU or pure-Python fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librebop_b200.so")
+
+OK, ERR_INVALID, ERR_OUT_OF_RANGE, ERR_PARSE, ERR_MISSING_PARAM, ERR_CUDA, ERR_NVRTC, ERR_LIMIT, ERR_ITER_CAP = range(9)
+ARITH_API, ARITH_MACRO = 0, 1
+KERNEL_AUTO, KERNEL_TABLE, KERNEL_NVRTC = 0, 1, 2
+OPCODES = dict(const=0, species=1, neg=2, add=3, sub=4, mul=5, div=6, pow=7, max=8, min=9, exp=10)
+
+
+class ExprOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("index", C.c_int32), ("value", C.c_double)]
+
+
+class RebopError(RuntimeError):
+    """A non-zero rebop_status; `.status` holds the code."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C rebop_b200/csrc` (rebop_b200 has no CPU fallback)")
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_vp = C.c_void_p
+_pp = C.POINTER(C.c_void_p)
+_u32p = C.POINTER(C.c_uint32)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u64p = C.POINTER(C.c_uint64)
+_f64p = C.POINTER(C.c_double)
+_szp = C.POINTER(C.c_size_t)
+
+# name -> (restype, argtypes); every symbol of include/rebop_b200.h
+SIGNATURES = {
+    "rebop_b200_last_error": (C.c_char_p, []),
+    "rebop_b200_version": (C.c_char_p, []),
+    "rebop_b200_device_count": (C.c_int, []),
+    "rebop_network_create": (C.c_int, [C.c_uint32, C.c_int, _pp]),
+    "rebop_network_destroy": (None, [_vp]),
+    "rebop_network_add_reaction_lma": (C.c_int, [_vp, C.c_double, _u32p, _i64p]),
+    "rebop_network_add_reaction_lma_sparse": (C.c_int, [_vp, C.c_double, _u32p, _u32p, C.c_size_t, _i64p]),
+    "rebop_network_add_reaction_expr": (C.c_int, [_vp, C.POINTER(ExprOp), C.c_size_t, _i64p]),
+    "rebop_network_nb_species": (C.c_int, [_vp, _u32p]),
+    "rebop_network_nb_reactions": (C.c_int, [_vp, _u32p]),
+    "rebop_network_codegen": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_network_jit_cubin": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_pexpr_parse": (C.c_int, [C.c_char_p, _pp]),
+    "rebop_pexpr_destroy": (None, [_vp]),
+    "rebop_pexpr_format": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_pexpr_lower": (C.c_int, [_vp, C.POINTER(C.c_char_p), C.c_size_t, C.POINTER(C.c_char_p), _f64p, C.c_size_t,
+                                    C.POINTER(ExprOp), C.c_size_t, _szp]),
+    "rebop_batch_create": (C.c_int, [_vp, C.c_int, C.c_size_t, _i64p, C.c_int, _u64p, C.c_uint64, _pp]),
+    "rebop_batch_destroy": (None, [_vp]),
+    "rebop_batch_set_kernel": (C.c_int, [_vp, C.c_int]),
+    "rebop_batch_get_kernel": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "rebop_batch_set_max_iters": (C.c_int, [_vp, C.c_uint32]),
+    "rebop_batch_seed": (C.c_int, [_vp, _u64p, C.c_uint64]),
+    "rebop_batch_get_time": (C.c_int, [_vp, _f64p]),
+    "rebop_batch_set_time": (C.c_int, [_vp, C.c_double]),
+    "rebop_batch_get_species": (C.c_int, [_vp, _i64p]),
+    "rebop_batch_set_species": (C.c_int, [_vp, _i64p, C.c_int]),
+    "rebop_batch_advance_until": (C.c_int, [_vp, C.c_double]),
+    "rebop_batch_run_grid": (C.c_int, [_vp, C.c_double, C.c_uint32, _u32p, C.c_uint32, _i32p]),
+    "rebop_batch_samples_device": (C.c_int, [_vp, C.POINTER(C.c_void_p), _szp, _u32p]),
+    "rebop_batch_samples_host_i32": (C.c_int, [_vp, _i32p]),
+    "rebop_batch_samples_host_i64": (C.c_int, [_vp, _i64p]),
+    "rebop_batch_sample_sums": (C.c_int, [_vp, _i64p, _u64p]),
+    "rebop_batch_sample_sums_device": (C.c_int, [_vp, C.POINTER(C.c_void_p), _u32p]),
+    "rebop_batch_events": (C.c_int, [_vp, _u64p, _u64p]),
+    "rebop_batch_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "rebop_batch_size": (C.c_int, [_vp, _szp]),
+    "rebop_batch_synchronize": (C.c_int, [_vp]),
+    "rebop_b200_measure_fp64_rate": (C.c_int, [C.c_int, _f64p, _f64p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return lib.rebop_b200_last_error().decode("utf-8", "replace")
+
+
+def check(status: int) -> None:
+    if status != OK:
+        raise RebopError(status, last_error())
+
+
+def ptr(a: np.ndarray, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def device_count() -> int:
+    return int(lib.rebop_b200_device_count())
+
+
+def make_program(ops) -> "C.Array[ExprOp]":
+    """ops: iterable of (opcode or name, index, value) in post-order."""
+    ops = list(ops)
+    arr = (ExprOp * max(1, len(ops)))()
+    for i, (op, idx, val) in enumerate(ops):
+        arr[i].op = OPCODES[op] if isinstance(op, str) else int(op)
+        arr[i].index = int(idx)
+        arr[i].value = float(val)
+    return arr
+
+
+class PExpr:
+    """A parsed rate expression (the reference's PExpr)."""
+
+    def __init__(self, text: str):
+        h = C.c_void_p()
+        check(lib.rebop_pexpr_parse(text.encode("utf-8"), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.rebop_pexpr_destroy(self._h)
+            self._h = None
+
+    def __str__(self) -> str:
+        need = C.c_size_t()
+        check(lib.rebop_pexpr_format(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(lib.rebop_pexpr_format(self._h, buf, need.value, None))
+        return buf.value.decode("utf-8")
+
+    def lower(self, species_names, params) -> list:
+        """-> [(op, index, value), ...] post-order program (PExpr::to_expr)."""
+        sn = (C.c_char_p * max(1, len(species_names)))(*[s.encode("utf-8") for s in species_names])
+        pn_list = list(params.keys())
+        pn = (C.c_char_p * max(1, len(pn_list)))(*[s.encode("utf-8") for s in pn_list])
+        pv = np.ascontiguousarray([float(params[k]) for k in pn_list] or [0.0], dtype=np.float64)
+        n = C.c_size_t()
+        check(lib.rebop_pexpr_lower(self._h, sn, len(species_names), pn, ptr(pv, C.c_double), len(pn_list), None, 0, C.byref(n)))
+        prog = (ExprOp * max(1, n.value))()
+        check(lib.rebop_pexpr_lower(self._h, sn, len(species_names), pn, ptr(pv, C.c_double), len(pn_list), prog, n.value, C.byref(n)))
+        return [(prog[i].op, prog[i].index, prog[i].value) for i in range(n.value)]
+
+
+class Network:
+    """Owning wrapper of a rebop_network handle."""
+
+    def __init__(self, n_species: int, arith: int = ARITH_API):
+        h = C.c_void_p()
+        check(lib.rebop_network_create(int(n_species), int(arith), C.byref(h)))
+        self._h = h
+        self.n_species = int(n_species)
+        self.arith = int(arith)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.rebop_network_destroy(self._h)
+            self._h = None
+
+    def _diff(self, differences) -> np.ndarray:
+        d = np.ascontiguousarray(differences, dtype=np.int64)
+        if d.shape != (self.n_species,):
+            raise RebopError(ERR_INVALID, "assertion failed: differences.len() == nb_species")
+        return d
+
+    def add_reaction_lma(self, k: float, exponents, differences) -> None:
+        e = np.ascontiguousarray(exponents, dtype=np.uint32)
+        if e.shape != (self.n_species,):
+            raise RebopError(ERR_INVALID, "assertion failed: stoechiometries.len() == nb_species")
+        d = self._diff(differences)
+        check(lib.rebop_network_add_reaction_lma(self._h, float(k), ptr(e, C.c_uint32), ptr(d, C.c_int64)))
+
+    def add_reaction_lma_sparse(self, k: float, terms, differences) -> None:
+        idx = np.ascontiguousarray([t[0] for t in terms] or [0], dtype=np.uint32)
+        ex = np.ascontiguousarray([t[1] for t in terms] or [0], dtype=np.uint32)
+        d = self._diff(differences)
+        check(lib.rebop_network_add_reaction_lma_sparse(self._h, float(k), ptr(idx, C.c_uint32), ptr(ex, C.c_uint32),
+                                                        len(terms), ptr(d, C.c_int64)))
+
+    def add_reaction_expr(self, program, differences) -> None:
+        program = list(program)
+        d = self._diff(differences)
+        check(lib.rebop_network_add_reaction_expr(self._h, make_program(program), len(program), ptr(d, C.c_int64)))
+
+    @property
+    def nb_reactions(self) -> int:
+        n = C.c_uint32()
+        check(lib.rebop_network_nb_reactions(self._h, C.byref(n)))
+        return n.value
+
+    def codegen(self) -> str:
+        need = C.c_size_t()
+        check(lib.rebop_network_codegen(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(lib.rebop_network_codegen(self._h, buf, need.value, None))
+        return buf.value.decode("utf-8")
+
+    def jit_cubin(self) -> bytes:
+        need = C.c_size_t()
+        check(lib.rebop_network_jit_cubin(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(lib.rebop_network_jit_cubin(self._h, buf, need.value, None))
+        return buf.raw
+
+
+class Batch:
+    """Owning wrapper of a rebop_batch handle: N trajectories resident on one GPU."""
+
+    def __init__(self, net: Network, n_traj: int, x0, seeds=None, seed_base: int = 0, device: int = 0,
+                 kernel: int = KERNEL_AUTO):
+        x0a = np.ascontiguousarray(x0, dtype=np.int64)
+        per_traj = 1 if x0a.ndim == 2 else 0
+        if per_traj and x0a.shape != (n_traj, net.n_species):
+            raise RebopError(ERR_INVALID, "x0 must be [n_species] or [n_traj][n_species]")
+        if not per_traj and x0a.shape != (net.n_species,):
+            raise RebopError(ERR_INVALID, "assertion failed: species.len() == nb_species")
+        sp = None
+        if seeds is not None:
+            self._seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+            if self._seeds.shape != (n_traj,):
+                raise RebopError(ERR_INVALID, "seeds must have one entry per trajectory")
+            sp = ptr(self._seeds, C.c_uint64)
+        h = C.c_void_p()
+        check(lib.rebop_batch_create(net._h, int(device), int(n_traj), ptr(x0a, C.c_int64) if x0a.size else None, per_traj, sp,
+                                     C.c_uint64(int(seed_base) & (2**64 - 1)), C.byref(h)))
+        self._h = h
+        self.net = net
+        self.n_traj = int(n_traj)
+        self.rows = 0
+        self.n_save = 0
+        if kernel != KERNEL_AUTO:
+            self.set_kernel(kernel)
+
+    def __del__(self):
+        self.close()
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.rebop_batch_destroy(self._h)
+            self._h = None
+
+    def set_kernel(self, kind: int) -> None:
+        check(lib.rebop_batch_set_kernel(self._h, int(kind)))
+
+    @property
+    def kernel_used(self) -> int:
+        k = C.c_int()
+        check(lib.rebop_batch_get_kernel(self._h, C.byref(k)))
+        return k.value
+
+    def set_max_iters(self, n: int) -> None:
+        check(lib.rebop_batch_set_max_iters(self._h, int(n)))
+
+    def seed(self, seeds=None, seed_base: int = 0) -> None:
+        if seeds is None:
+            check(lib.rebop_batch_seed(self._h, None, C.c_uint64(int(seed_base))))
+        else:
+            s = np.ascontiguousarray(seeds, dtype=np.uint64)
+            check(lib.rebop_batch_seed(self._h, ptr(s, C.c_uint64), 0))
+
+    def advance_until(self, tmax: float) -> None:
+        check(lib.rebop_batch_advance_until(self._h, float(tmax)))
+
+    def run_grid(self, tmax: float, nb_steps: int, save_idx=None, host_out: np.ndarray | None = None) -> None:
+        n_save = self.net.n_species if save_idx is None else len(save_idx)
+        sp = None
+        if save_idx is not None:
+            sv = np.ascontiguousarray(save_idx, dtype=np.uint32)
+            sp = ptr(sv, C.c_uint32)
+        hp = None
+        if host_out is not None:
+            assert host_out.dtype == np.int32 and host_out.flags.c_contiguous
+            assert host_out.size == (nb_steps + 1) * n_save * self.n_traj
+            hp = ptr(host_out, C.c_int32)
+        self.rows, self.n_save = (nb_steps + 1) * n_save, n_save
+        check(lib.rebop_batch_run_grid(self._h, float(tmax), int(nb_steps), sp, n_save, hp))
+
+    def samples(self, dtype=np.int32) -> np.ndarray:
+        """Samples of the last run_grid as [nb_steps+1][n_save][n_traj]."""
+        steps = self.rows // self.n_save if self.n_save else 0
+        out = np.empty((steps, self.n_save, self.n_traj), dtype=dtype)
+        if out.size:
+            if dtype == np.int32:
+                check(lib.rebop_batch_samples_host_i32(self._h, ptr(out, C.c_int32)))
+            elif dtype == np.int64:
+                check(lib.rebop_batch_samples_host_i64(self._h, ptr(out, C.c_int64)))
+            else:
+                raise TypeError("dtype must be int32 or int64")
+        return out
+
+    def samples_device(self):
+        """(device pointer, leading dimension in elements, rows) of the last run_grid's samples."""
+        p, ld, rows = C.c_void_p(), C.c_size_t(), C.c_uint32()
+        check(lib.rebop_batch_samples_device(self._h, C.byref(p), C.byref(ld), C.byref(rows)))
+        return p.value, ld.value, rows.value
+
+    def sample_sums(self):
+        sums = np.zeros(self.rows, dtype=np.int64)
+        sq = np.zeros(self.rows, dtype=np.uint64)
+        check(lib.rebop_batch_sample_sums(self._h, ptr(sums, C.c_int64), ptr(sq, C.c_uint64)))
+        return sums, sq
+
+    def sample_sums_device(self):
+        p, rows = C.c_void_p(), C.c_uint32()
+        check(lib.rebop_batch_sample_sums_device(self._h, C.byref(p), C.byref(rows)))
+        return p.value, rows.value
+
+    def species(self) -> np.ndarray:
+        out = np.empty((self.n_traj, self.net.n_species), dtype=np.int64)
+        if out.size:
+            check(lib.rebop_batch_get_species(self._h, ptr(out, C.c_int64)))
+        return out
+
+    def set_species(self, species) -> None:
+        a = np.ascontiguousarray(species, dtype=np.int64)
+        check(lib.rebop_batch_set_species(self._h, ptr(a, C.c_int64), 1 if a.ndim == 2 else 0))
+
+    def times(self) -> np.ndarray:
+        out = np.empty(self.n_traj, dtype=np.float64)
+        check(lib.rebop_batch_get_time(self._h, ptr(out, C.c_double)))
+        return out
+
+    def set_time(self, t: float) -> None:
+        check(lib.rebop_batch_set_time(self._h, float(t)))
+
+    def events(self):
+        tot, last = C.c_uint64(), C.c_uint64()
+        check(lib.rebop_batch_events(self._h, C.byref(tot), C.byref(last)))
+        return tot.value, last.value
+
+    @property
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(lib.rebop_batch_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self) -> None:
+        check(lib.rebop_batch_synchronize(self._h))
+
+
+def measure_fp64_rate(device: int = 0):
+    ops, mhz = C.c_double(), C.c_double()
+    check(lib.rebop_b200_measure_fp64_rate(int(device), C.byref(ops), C.byref(mhz)))
+    return ops.value, mhz.value

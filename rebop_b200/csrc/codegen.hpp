@@ -1,0 +1,20 @@
+// codegen.hpp -- network -> CUDA source of a network-specialised ensemble kernel.
+#pragma once
+#include <string>
+
+#include "network.hpp"
+
+// Register-resident state and cumulative sums bound the networks that can be specialised;
+// larger ones use the table-driven kernel (shared-memory state).
+#define RB_GEN_MAX_SPECIES 32
+#define RB_GEN_MAX_REACTIONS 48
+
+struct RbCodegenInfo {
+  unsigned block = 128;      // threads per CTA the kernel was generated for
+  unsigned net_words = 0;    // 32-bit words of shared memory for the packed stoichiometry table
+  bool uses_param_k = true;  // LMA rate constants are read from SsaRunParams::k
+};
+
+bool rb_codegen_supported(const rebop_network& net, std::string* why);
+// Source text of `extern "C" __global__ void <kernel_name>(SsaRunParams)`; includes "ssa_kernel.cuh".
+std::string rb_codegen_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info);

@@ -1,0 +1,584 @@
+// engine.cu -- device-resident ensembles ("batches") and the launches that advance them.
+//
+// A batch is N instances of the reference's `Gillespie` struct (src/gillespie.rs:157-163)
+// laid out for the GPU: species x[S][ldn] (int32, trajectory-contiguous), time t[ldn],
+// xoshiro256++ state rng[4][ldn].  State persists between calls so that repeated
+// advance_until / run_grid calls continue the same random streams, exactly like repeated
+// calls on the CPU struct.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "jit.hpp"
+#include "network.hpp"
+#include "ssa_params.h"
+#include "ssa_table.h"
+
+#define RB_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t err__ = (call);                                                                \
+    if (err__ != cudaSuccess)                                                                  \
+      return rb_fail(REBOP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));   \
+  } while (0)
+
+struct rebop_batch {
+  rebop_network net;
+  int device = 0;
+  size_t n = 0, ldn = 0;
+  int* d_x = nullptr;
+  double* d_t = nullptr;
+  rb_u64* d_rng = nullptr;
+  rb_u64* d_seeds = nullptr;
+  rb_u64 seed_base = 0;
+  unsigned seed_mode = 0;  // pending seeding for the next launch (0 = streams already live)
+  int* d_out = nullptr;
+  size_t out_capacity = 0;  // int32 elements
+  uint32_t out_rows = 0;    // (nb_steps+1) * n_save of the last run_grid
+  uint32_t out_n_save = 0, out_nb_steps = 0;
+  rb_u64* d_counters = nullptr;  // [0] events, [1] status (low 32 bits)
+  rb_i64* d_sums = nullptr;
+  size_t sums_capacity = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint64_t events_total = 0, events_last = 0;
+  int kernel_pref = REBOP_KERNEL_AUTO, kernel_used = REBOP_KERNEL_AUTO;
+  uint32_t max_iters = 0;
+  float last_ms = 0.f;
+  RbTables tables;
+  bool tables_ok = false;
+  std::string tables_error;
+  int max_smem_optin = 0, sm_count = 0;
+};
+
+// ---------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------
+__global__ void rb_fill_state_kernel(int* x, double* t, const int* x0, unsigned n_species,
+                                     unsigned ldn, unsigned n, double t0, int fill_x, int fill_t) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ldn) return;
+  if (fill_x)
+    for (unsigned s = 0; s < n_species; ++s) x[(size_t)s * ldn + i] = i < n ? x0[s] : 0;
+  if (fill_t) t[i] = t0;
+}
+
+// K4: exact integer sum and sum of squares of every sample row over the trajectories.
+// rows are 128-byte aligned (ldn % 32 == 0); one CTA reduces a segment of one row.
+__global__ void __launch_bounds__(256) rb_row_sums_kernel(const int* __restrict__ samples, unsigned n,
+                                                          unsigned ldn, rb_i64* __restrict__ sums,
+                                                          unsigned n_rows) {
+  const unsigned row = blockIdx.y;
+  const int4* src = reinterpret_cast<const int4*>(samples + (size_t)row * ldn);
+  const unsigned n4 = n / 4u;
+  rb_i64 s1 = 0;
+  rb_u64 s2 = 0;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int4 v = __ldcs(src + i);
+    s1 += (rb_i64)v.x + v.y + v.z + v.w;
+    s2 += (rb_u64)((rb_i64)v.x * v.x) + (rb_u64)((rb_i64)v.y * v.y) + (rb_u64)((rb_i64)v.z * v.z) +
+          (rb_u64)((rb_i64)v.w * v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) {
+    const int v = samples[(size_t)row * ldn + n4 * 4u + threadIdx.x];
+    s1 += v;
+    s2 += (rb_u64)((rb_i64)v * v);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    s1 += __shfl_down_sync(0xffffffffu, s1, off);
+    s2 += __shfl_down_sync(0xffffffffu, s2, off);
+  }
+  __shared__ rb_i64 w1[8];
+  __shared__ rb_u64 w2[8];
+  if ((threadIdx.x & 31u) == 0) {
+    w1[threadIdx.x >> 5] = s1;
+    w2[threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      s1 += w1[w];
+      s2 += w2[w];
+    }
+    atomicAdd(reinterpret_cast<rb_u64*>(sums) + row, (rb_u64)s1);
+    atomicAdd(reinterpret_cast<rb_u64*>(sums) + n_rows + row, s2);
+  }
+}
+
+// FP64 issue-rate probe: 8 independent chains per thread, alternating non-fused add / multiply.
+__global__ void __launch_bounds__(256) rb_fp64_probe_kernel(double* sink, int iters, long long* clocks) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+  double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+  const double m = 1.0 - 1e-12, c = 1e-12;
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a0 = __dmul_rn(a0, m); a1 = __dadd_rn(a1, c); a2 = __dmul_rn(a2, m); a3 = __dadd_rn(a3, c);
+      a4 = __dmul_rn(a4, m); a5 = __dadd_rn(a5, c); a6 = __dmul_rn(a6, m); a7 = __dadd_rn(a7, c);
+    }
+  }
+  const long long t1 = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = t1 - t0;
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+static int select_device(int device) {
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0)
+    return rb_fail(REBOP_ERR_CUDA, std::string("no CUDA device available (this engine has no CPU fallback): ") +
+                                       (err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0"));
+  if (device < 0 || device >= count) return rb_fail(REBOP_ERR_INVALID, "device index out of range");
+  RB_CUDA(cudaSetDevice(device));
+  return REBOP_OK;
+}
+
+extern "C" int rebop_b200_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+
+static int upload_x0(rebop_batch* b, const int64_t* x0, int per_traj) {
+  const uint32_t S = b->net.n_species;
+  if (S == 0) return REBOP_OK;
+  if (!x0) return rb_fail(REBOP_ERR_INVALID, "x0 is NULL");
+  const size_t count = per_traj ? b->n * S : S;
+  for (size_t i = 0; i < count; ++i)
+    if (x0[i] < INT32_MIN || x0[i] > INT32_MAX)
+      return rb_fail(REBOP_ERR_LIMIT, "initial species count outside the int32 range carried on the device");
+  if (!per_traj) {
+    std::vector<int> h(S);
+    for (uint32_t s = 0; s < S; ++s) h[s] = (int)x0[s];
+    int* d_x0 = nullptr;
+    RB_CUDA(cudaMallocAsync(&d_x0, S * sizeof(int), b->stream));
+    RB_CUDA(cudaMemcpyAsync(d_x0, h.data(), S * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    rb_fill_state_kernel<<<(unsigned)((b->ldn + 255) / 256), 256, 0, b->stream>>>(
+        b->d_x, b->d_t, d_x0, S, (unsigned)b->ldn, (unsigned)b->n, 0.0, 1, 0);
+    RB_CUDA(cudaGetLastError());
+    RB_CUDA(cudaStreamSynchronize(b->stream));  // h goes out of scope
+    RB_CUDA(cudaFreeAsync(d_x0, b->stream));
+  } else {
+    std::vector<int> h((size_t)S * b->ldn, 0);
+    for (size_t n = 0; n < b->n; ++n)
+      for (uint32_t s = 0; s < S; ++s) h[(size_t)s * b->ldn + n] = (int)x0[n * S + s];
+    RB_CUDA(cudaMemcpyAsync(b->d_x, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    RB_CUDA(cudaStreamSynchronize(b->stream));
+  }
+  return REBOP_OK;
+}
+
+static int upload_seeds(rebop_batch* b, const uint64_t* seeds, uint64_t seed_base) {
+  if (seeds) {
+    if (!b->d_seeds) RB_CUDA(cudaMalloc(&b->d_seeds, b->ldn * sizeof(rb_u64)));
+    RB_CUDA(cudaMemcpyAsync(b->d_seeds, seeds, b->n * sizeof(rb_u64), cudaMemcpyHostToDevice, b->stream));
+    RB_CUDA(cudaStreamSynchronize(b->stream));
+    b->seed_mode = 1;
+  } else {
+    b->seed_base = seed_base;
+    b->seed_mode = 2;
+  }
+  return REBOP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batch life cycle
+// ---------------------------------------------------------------------------
+extern "C" void rebop_batch_destroy(rebop_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  cudaFree(b->d_x); cudaFree(b->d_t); cudaFree(b->d_rng); cudaFree(b->d_seeds);
+  cudaFree(b->d_out); cudaFree(b->d_counters); cudaFree(b->d_sums);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+extern "C" int rebop_batch_create(const rebop_network* net, int device, size_t n_traj, const int64_t* x0,
+                                  int x0_per_trajectory, const uint64_t* seeds, uint64_t seed_base,
+                                  rebop_batch** out) {
+  if (!net || !out) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  if (n_traj == 0 || n_traj > 0x7fffffffu) return rb_fail(REBOP_ERR_INVALID, "n_traj must be in [1, 2^31)");
+  int st = select_device(device);
+  if (st) return st;
+  rebop_batch* b = new rebop_batch();
+  b->net = *net;
+  b->device = device;
+  b->n = n_traj;
+  b->ldn = (n_traj + 31) / 32 * 32;
+  st = rb_lower_tables(b->net, &b->tables);
+  b->tables_ok = (st == REBOP_OK);
+  if (!b->tables_ok) b->tables_error = rebop_b200_last_error();
+#define RB_CREATE_CUDA(call)                                                                     \
+  do {                                                                                           \
+    cudaError_t err__ = (call);                                                                  \
+    if (err__ != cudaSuccess) {                                                                  \
+      rb_set_error(std::string(#call) + ": " + cudaGetErrorString(err__));                       \
+      rebop_batch_destroy(b);                                                                    \
+      return REBOP_ERR_CUDA;                                                                     \
+    }                                                                                            \
+  } while (0)
+  const size_t S = net->n_species ? net->n_species : 1;
+  RB_CREATE_CUDA(cudaDeviceGetAttribute(&b->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  RB_CREATE_CUDA(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
+  RB_CREATE_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  RB_CREATE_CUDA(cudaEventCreate(&b->ev0));
+  RB_CREATE_CUDA(cudaEventCreate(&b->ev1));
+  RB_CREATE_CUDA(cudaMalloc(&b->d_x, S * b->ldn * sizeof(int)));
+  RB_CREATE_CUDA(cudaMalloc(&b->d_t, b->ldn * sizeof(double)));
+  RB_CREATE_CUDA(cudaMalloc(&b->d_rng, 4 * b->ldn * sizeof(rb_u64)));
+  RB_CREATE_CUDA(cudaMalloc(&b->d_counters, 2 * sizeof(rb_u64)));
+  RB_CREATE_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(rb_u64), b->stream));
+  RB_CREATE_CUDA(cudaMemsetAsync(b->d_rng, 0, 4 * b->ldn * sizeof(rb_u64), b->stream));
+  RB_CREATE_CUDA(cudaMemsetAsync(b->d_t, 0, b->ldn * sizeof(double), b->stream));
+  RB_CREATE_CUDA(cudaMemsetAsync(b->d_x, 0, S * b->ldn * sizeof(int), b->stream));
+#undef RB_CREATE_CUDA
+  st = upload_x0(b, x0, x0_per_trajectory);
+  if (!st) st = upload_seeds(b, seeds, seed_base);
+  if (st) {
+    rebop_batch_destroy(b);
+    return st;
+  }
+  *out = b;
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_set_kernel(rebop_batch* b, int kind) {
+  if (!b || kind < REBOP_KERNEL_AUTO || kind > REBOP_KERNEL_NVRTC) return rb_fail(REBOP_ERR_INVALID, "bad kernel kind");
+  b->kernel_pref = kind;
+  return REBOP_OK;
+}
+extern "C" int rebop_batch_get_kernel(const rebop_batch* b, int* kind) {
+  if (!b || !kind) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  *kind = b->kernel_used;
+  return REBOP_OK;
+}
+extern "C" int rebop_batch_set_max_iters(rebop_batch* b, uint32_t max_iters) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  b->max_iters = max_iters;
+  return REBOP_OK;
+}
+extern "C" int rebop_batch_size(const rebop_batch* b, size_t* n_traj) {
+  if (!b || !n_traj) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  *n_traj = b->n;
+  return REBOP_OK;
+}
+extern "C" int rebop_batch_synchronize(rebop_batch* b) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_seed(rebop_batch* b, const uint64_t* seeds, uint64_t seed_base) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  return upload_seeds(b, seeds, seed_base);
+}
+
+extern "C" int rebop_batch_get_time(rebop_batch* b, double* t) {
+  if (!b || !t) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  RB_CUDA(cudaMemcpyAsync(t, b->d_t, b->n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_set_time(rebop_batch* b, double t) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  rb_fill_state_kernel<<<(unsigned)((b->ldn + 255) / 256), 256, 0, b->stream>>>(
+      b->d_x, b->d_t, nullptr, 0, (unsigned)b->ldn, (unsigned)b->n, t, 0, 1);
+  RB_CUDA(cudaGetLastError());
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_get_species(rebop_batch* b, int64_t* species) {
+  if (!b || !species) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  const uint32_t S = b->net.n_species;
+  std::vector<int> h((size_t)S * b->ldn);
+  RB_CUDA(cudaMemcpyAsync(h.data(), b->d_x, h.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  for (size_t n = 0; n < b->n; ++n)
+    for (uint32_t s = 0; s < S; ++s) species[n * S + s] = h[(size_t)s * b->ldn + n];
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_set_species(rebop_batch* b, const int64_t* species, int per_trajectory) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  return upload_x0(b, species, per_trajectory);
+}
+
+// ---------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------
+static unsigned pow2_floor(unsigned v) {
+  unsigned p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+// Ring depth: as many grid points as fit next to the kernel's other shared memory while leaving
+// room for `ctas_per_sm` resident CTAs; a power of two in [1, 32], no deeper than the grid.
+static unsigned choose_ring_depth(const rebop_batch* b, unsigned block, unsigned net_words, unsigned n_save,
+                                  unsigned n_points, unsigned ctas_per_sm) {
+  if (n_save == 0) return 1;
+  const size_t fixed = 4u * (4u * RB_ZIG_STRIDE + net_words);
+  const size_t per_depth = (size_t)(block / 32u) * n_save * 32u * 4u;
+  const size_t budget = (size_t)b->max_smem_optin / (ctas_per_sm ? ctas_per_sm : 1);
+  unsigned depth = 1;
+  if (budget > fixed + per_depth) depth = (unsigned)std::min<size_t>(32, (budget - fixed) / per_depth);
+  depth = pow2_floor(depth ? depth : 1);
+  unsigned cap = 1;
+  while (cap < n_points && cap < 32) cap *= 2;
+  return std::min(depth, cap);
+}
+
+static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_first, uint32_t step_last,
+                  int* d_out, uint32_t n_save, const uint32_t* save_idx) {
+  const uint32_t S = b->net.n_species;
+  SsaRunParams p;
+  std::memset(&p, 0, sizeof p);
+  p.x = b->d_x;
+  p.t = b->d_t;
+  p.rng = b->d_rng;
+  p.seeds = b->d_seeds;
+  p.seed_base = b->seed_base;
+  p.out = d_out;
+  p.events = b->d_counters;
+  p.status = reinterpret_cast<rb_u32*>(b->d_counters + 1);
+  p.tmax = tmax;
+  p.n_traj = (rb_u32)b->n;
+  p.ldn = (rb_u32)b->ldn;
+  p.nb_steps = nb_steps;
+  p.step_first = step_first;
+  p.step_last = step_last;
+  p.n_save = d_out ? n_save : 0;
+  p.seed_mode = b->seed_mode;
+  p.max_iters = b->max_iters;
+  const unsigned n_points = step_last - step_first + 1;
+
+  RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(rb_u64), b->stream));
+
+  // --- pick the kernel ---
+  RbJitKernel jit;
+  bool use_jit = false;
+  if (b->kernel_pref != REBOP_KERNEL_TABLE) {
+    int st = rb_jit_get(b->net, b->device, &jit);
+    if (st == REBOP_OK) {
+      use_jit = true;
+    } else if (b->kernel_pref == REBOP_KERNEL_NVRTC) {
+      return st;
+    }
+  }
+
+  RB_CUDA(cudaEventRecord(b->ev0, b->stream));
+  if (use_jit) {
+    // saved species: the specialised kernels take a bit mask and emit rows in ascending species order
+    for (uint32_t j = 0; j < p.n_save; ++j) p.save_mask[save_idx[j] >> 6] |= 1ull << (save_idx[j] & 63u);
+    for (size_t r = 0; r < b->net.rx.size() && r < 64; ++r) p.k[r] = b->net.rx[r].k;
+    const unsigned block = jit.block;
+    const unsigned ctas = std::max(1u, 2048u / block / 2u);
+    p.ring_depth = choose_ring_depth(b, block, jit.net_words, p.n_save, n_points, ctas);
+    const size_t smem = RB_SSA_SMEM_BYTES(jit.net_words, block, p.ring_depth, p.n_save);
+    const unsigned grid = (unsigned)((b->n + block - 1) / block);
+    int st = rb_jit_launch(jit, p, grid, smem, b->stream);
+    if (st) return st;
+    b->kernel_used = REBOP_KERNEL_NVRTC;
+  } else {
+    if (!b->tables_ok) return rb_fail(REBOP_ERR_LIMIT, b->tables_error);
+    if (p.n_save > RB_TAB_MAX_SAVE) return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: more than 1024 saved species");
+    for (uint32_t j = 0; j < p.n_save; ++j) b->tables.save_idx[j] = (unsigned short)save_idx[j];
+    const unsigned block = RB_TABLE_BLOCK;
+    const unsigned net_words = S * block;
+    p.ring_depth = choose_ring_depth(b, block, net_words, p.n_save, n_points, 8);
+    const size_t smem = RB_SSA_SMEM_BYTES(net_words, block, p.ring_depth, p.n_save);
+    if (smem > (size_t)b->max_smem_optin)
+      return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: species state and sample ring do not fit in shared memory");
+    const unsigned grid = (unsigned)((b->n + block - 1) / block);
+    RB_CUDA(rb_table_launch(&b->tables, p, grid, smem, b->stream));
+    b->kernel_used = REBOP_KERNEL_TABLE;
+  }
+  RB_CUDA(cudaEventRecord(b->ev1, b->stream));
+
+  rb_u64 counters[2] = {0, 0};
+  RB_CUDA(cudaMemcpyAsync(counters, b->d_counters, sizeof counters, cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  RB_CUDA(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
+  b->seed_mode = 0;  // streams are live on the device from now on
+  b->events_last = counters[0];
+  b->events_total += counters[0];
+  if (counters[1] & RB_STATUS_ITER_CAP)
+    return rb_fail(REBOP_ERR_ITER_CAP, "a trajectory hit the per-launch iteration cap before reaching its target time");
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_advance_until(rebop_batch* b, double tmax) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  return launch(b, tmax, 0, 0, 0, nullptr, 0, nullptr);
+}
+
+extern "C" int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
+                                    uint32_t n_save, int32_t* host_out) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  if (nb_steps == 0) return rb_fail(REBOP_ERR_INVALID, "run_grid needs nb_steps >= 1 (nb_steps = 0 is the event-log mode)");
+  RB_CUDA(cudaSetDevice(b->device));
+  const uint32_t S = b->net.n_species;
+  std::vector<uint32_t> all;
+  if (!save_idx) {
+    all.resize(S);
+    for (uint32_t s = 0; s < S; ++s) all[s] = s;
+    save_idx = all.data();
+    n_save = S;
+  }
+  for (uint32_t j = 0; j < n_save; ++j)
+    if (save_idx[j] >= S) return rb_fail(REBOP_ERR_OUT_OF_RANGE, "save_idx refers to a species index out of range");
+  const size_t rows = (size_t)(nb_steps + 1) * n_save;
+  const size_t need = std::max<size_t>(1, rows * b->ldn);
+  if (need > b->out_capacity) {
+    if (b->d_out) RB_CUDA(cudaFree(b->d_out));
+    b->d_out = nullptr;
+    b->out_capacity = 0;
+    RB_CUDA(cudaMalloc(&b->d_out, need * sizeof(int)));
+    b->out_capacity = need;
+  }
+  b->out_rows = (uint32_t)rows;
+  b->out_n_save = n_save;
+  b->out_nb_steps = nb_steps;
+  int st = launch(b, tmax, nb_steps, 0, nb_steps, n_save ? b->d_out : nullptr, n_save, save_idx);
+  if (st) return st;
+  if (host_out) return rebop_batch_samples_host_i32(b, host_out);
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_samples_device(const rebop_batch* b, const int32_t** dev_ptr, size_t* ld,
+                                          uint32_t* n_rows) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  if (dev_ptr) *dev_ptr = b->d_out;
+  if (ld) *ld = b->ldn;
+  if (n_rows) *n_rows = b->out_rows;
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_samples_host_i32(rebop_batch* b, int32_t* out) {
+  if (!b || !out) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  if (b->out_rows == 0) return REBOP_OK;
+  RB_CUDA(cudaSetDevice(b->device));
+  RB_CUDA(cudaMemcpy2DAsync(out, b->n * sizeof(int), b->d_out, b->ldn * sizeof(int), b->n * sizeof(int),
+                            b->out_rows, cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_samples_host_i64(rebop_batch* b, int64_t* out) {
+  if (!b || !out) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  const size_t count = (size_t)b->out_rows * b->n;
+  std::vector<int32_t> tmp(count);
+  int st = rebop_batch_samples_host_i32(b, tmp.data());
+  if (st) return st;
+  for (size_t i = 0; i < count; ++i) out[i] = tmp[i];
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_sample_sums_device(rebop_batch* b, const int64_t** dev_ptr, uint32_t* n_rows) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  const uint32_t rows = b->out_rows;
+  if (rows == 0) return rb_fail(REBOP_ERR_INVALID, "no samples: call run_grid first");
+  if (2u * rows > b->sums_capacity) {
+    if (b->d_sums) RB_CUDA(cudaFree(b->d_sums));
+    b->d_sums = nullptr;
+    RB_CUDA(cudaMalloc(&b->d_sums, 2 * (size_t)rows * sizeof(rb_i64)));
+    b->sums_capacity = 2u * rows;
+  }
+  RB_CUDA(cudaMemsetAsync(b->d_sums, 0, 2 * (size_t)rows * sizeof(rb_i64), b->stream));
+  // enough CTAs per row to fill the machine, each thread moving 16 bytes per load
+  const unsigned per_row = (unsigned)std::max<size_t>(1, std::min<size_t>((b->n / 4 + 255) / 256,
+                                                        std::max<size_t>(1, (size_t)b->sm_count * 8 / rows + 1)));
+  dim3 grid(per_row, rows);
+  rb_row_sums_kernel<<<grid, 256, 0, b->stream>>>(b->d_out, (unsigned)b->n, (unsigned)b->ldn, b->d_sums, rows);
+  RB_CUDA(cudaGetLastError());
+  if (dev_ptr) *dev_ptr = reinterpret_cast<const int64_t*>(b->d_sums);
+  if (n_rows) *n_rows = rows;
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_sample_sums(rebop_batch* b, int64_t* sum, uint64_t* sumsq) {
+  if (!b || !sum || !sumsq) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  const int64_t* d = nullptr;
+  uint32_t rows = 0;
+  int st = rebop_batch_sample_sums_device(b, &d, &rows);
+  if (st) return st;
+  RB_CUDA(cudaMemcpyAsync(sum, d, rows * sizeof(int64_t), cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaMemcpyAsync(sumsq, d + rows, rows * sizeof(int64_t), cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_events(rebop_batch* b, uint64_t* total, uint64_t* last_launch) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  if (total) *total = b->events_total;
+  if (last_launch) *last_launch = b->events_last;
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_last_kernel_ms(rebop_batch* b, float* ms) {
+  if (!b || !ms) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  *ms = b->last_ms;
+  return REBOP_OK;
+}
+
+extern "C" int rebop_b200_measure_fp64_rate(int device, double* ops_per_second, double* sm_clock_mhz) {
+  int st = select_device(device);
+  if (st) return st;
+  int sms = 0;
+  RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  double* sink = nullptr;
+  long long* clocks = nullptr;
+  RB_CUDA(cudaMalloc(&sink, (size_t)blocks * threads * sizeof(double)));
+  RB_CUDA(cudaMalloc(&clocks, sizeof(long long)));
+  cudaEvent_t e0, e1;
+  RB_CUDA(cudaEventCreate(&e0));
+  RB_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  long long clk = 0;
+  for (int rep = 0; rep < 5; ++rep) {  // first pass warms up
+    RB_CUDA(cudaEventRecord(e0));
+    rb_fp64_probe_kernel<<<blocks, threads>>>(sink, iters, clocks);
+    RB_CUDA(cudaEventRecord(e1));
+    RB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    RB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) {
+      best = ms;
+      RB_CUDA(cudaMemcpy(&clk, clocks, sizeof clk, cudaMemcpyDeviceToHost));
+    }
+  }
+  RB_CUDA(cudaGetLastError());
+  const double ops = (double)blocks * threads * (double)iters * 32.0;
+  if (ops_per_second) *ops_per_second = ops / (best * 1e-3);
+  // one CTA's loop spans (almost) the whole kernel when every SM holds its 8 CTAs at once
+  if (sm_clock_mhz) *sm_clock_mhz = (double)clk / (best * 1e-3) / 1e6;
+  cudaFree(sink);
+  cudaFree(clocks);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return REBOP_OK;
+}

@@ -1,0 +1,178 @@
+// jit.cpp -- NVRTC compilation and loading of generated kernels.
+//
+// libnvrtc is opened with dlopen so that the library itself loads (and its host-side API works)
+// on machines without the CUDA toolkit; the cubin is loaded through the runtime's library API,
+// so there is no link-time dependency on the driver either.
+#include "jit.hpp"
+
+#include <dlfcn.h>
+
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "codegen.hpp"
+
+extern const char* const rb_embedded_names[];
+extern const char* const rb_embedded_sources[];
+extern const int rb_embedded_count;
+
+namespace {
+
+typedef struct _nvrtcProgram* nvrtcProgram;
+typedef int nvrtcResult;
+
+struct Nvrtc {
+  void* handle = nullptr;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  const char* (*GetErrorString)(nvrtcResult) = nullptr;
+  std::string error;
+};
+
+Nvrtc& nvrtc() {
+  static Nvrtc n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char* name : names) {
+      n.handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (n.handle) break;
+    }
+    if (!n.handle) {
+      n.error = "libnvrtc.so.12 not found";
+      return;
+    }
+#define RB_SYM(field, sym)                                             \
+  n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.handle, sym)); \
+  if (!n.field) n.error = std::string("missing NVRTC symbol ") + sym;
+    RB_SYM(CreateProgram, "nvrtcCreateProgram")
+    RB_SYM(CompileProgram, "nvrtcCompileProgram")
+    RB_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    RB_SYM(GetProgramLog, "nvrtcGetProgramLog")
+    RB_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    RB_SYM(GetCUBIN, "nvrtcGetCUBIN")
+    RB_SYM(DestroyProgram, "nvrtcDestroyProgram")
+    RB_SYM(GetErrorString, "nvrtcGetErrorString")
+#undef RB_SYM
+  });
+  return n;
+}
+
+struct CacheEntry {
+  cudaLibrary_t lib = nullptr;
+  RbJitKernel k;
+};
+std::mutex g_mutex;
+std::map<std::pair<int, std::string>, CacheEntry> g_cache;
+
+}  // namespace
+
+// NVRTC: source text -> sm_100a cubin.  Needs no GPU.
+static int compile_to_cubin(const std::string& src, std::vector<char>* cubin) {
+  Nvrtc& n = nvrtc();
+  if (!n.error.empty()) return rb_fail(REBOP_ERR_NVRTC, "NVRTC unavailable: " + n.error);
+  nvrtcProgram prog = nullptr;
+  nvrtcResult res = n.CreateProgram(&prog, src.c_str(), "rb_ssa_jit.cu", rb_embedded_count, rb_embedded_sources,
+                                    rb_embedded_names);
+  if (res != 0) return rb_fail(REBOP_ERR_NVRTC, std::string("nvrtcCreateProgram: ") + n.GetErrorString(res));
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-lineinfo", "--std=c++17"};
+  res = n.CompileProgram(prog, 4, opts);
+  if (res != 0) {
+    size_t log_size = 0;
+    n.GetProgramLogSize(prog, &log_size);
+    std::string log(log_size, '\0');
+    if (log_size) n.GetProgramLog(prog, &log[0]);
+    n.DestroyProgram(&prog);
+    return rb_fail(REBOP_ERR_NVRTC, std::string("nvrtcCompileProgram: ") + n.GetErrorString(res) + "\n" + log);
+  }
+  size_t cubin_size = 0;
+  n.GetCUBINSize(prog, &cubin_size);
+  cubin->resize(cubin_size);
+  res = n.GetCUBIN(prog, cubin->data());
+  n.DestroyProgram(&prog);
+  if (res != 0 || cubin_size == 0) return rb_fail(REBOP_ERR_NVRTC, "nvrtcGetCUBIN failed");
+  return REBOP_OK;
+}
+
+int rb_jit_compile(const rebop_network& net, std::string* source, std::vector<char>* cubin) {
+  std::string why;
+  if (!rb_codegen_supported(net, &why)) return rb_fail(REBOP_ERR_LIMIT, "network cannot be specialised: " + why);
+  RbCodegenInfo info;
+  const std::string src = rb_codegen_source(net, "rb_ssa_jit", &info);
+  if (source) *source = src;
+  if (cubin) return compile_to_cubin(src, cubin);
+  return REBOP_OK;
+}
+
+int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out) {
+  std::string why;
+  if (!rb_codegen_supported(net, &why)) return rb_fail(REBOP_ERR_LIMIT, "network cannot be specialised: " + why);
+  RbCodegenInfo info;
+  const std::string src = rb_codegen_source(net, "rb_ssa_jit", &info);
+
+  std::lock_guard<std::mutex> lock(g_mutex);
+  auto key = std::make_pair(device, src);
+  auto it = g_cache.find(key);
+  if (it != g_cache.end()) {
+    *out = it->second.k;
+    return REBOP_OK;
+  }
+  std::vector<char> cubin;
+  int st = compile_to_cubin(src, &cubin);
+  if (st) return st;
+
+  CacheEntry e;
+  cudaError_t err = cudaLibraryLoadData(&e.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(err));
+  cudaKernel_t kernel = nullptr;
+  err = cudaLibraryGetKernel(&kernel, e.lib, "rb_ssa_jit");
+  if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(err));
+  e.k.kernel = kernel;
+  e.k.block = info.block;
+  e.k.net_words = info.net_words;
+  g_cache[key] = e;
+  *out = e.k;
+  return REBOP_OK;
+}
+
+// ---- C ABI: inspection of the generated kernel (no GPU needed) ----
+static int copy_out(const char* data, size_t size, char* buf, size_t cap, size_t* needed) {
+  if (needed) *needed = size;
+  if (buf && cap) std::memcpy(buf, data, size < cap ? size : cap);
+  return REBOP_OK;
+}
+
+extern "C" int rebop_network_codegen(const rebop_network* net, char* buf, size_t cap, size_t* needed) {
+  if (!net) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  std::string src;
+  int st = rb_jit_compile(*net, &src, nullptr);
+  if (st) return st;
+  return copy_out(src.c_str(), src.size() + 1, buf, cap, needed);
+}
+
+extern "C" int rebop_network_jit_cubin(const rebop_network* net, char* buf, size_t cap, size_t* needed) {
+  if (!net) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  std::vector<char> cubin;
+  int st = rb_jit_compile(*net, nullptr, &cubin);
+  if (st) return st;
+  return copy_out(cubin.data(), cubin.size(), buf, cap, needed);
+}
+
+int rb_jit_launch(const RbJitKernel& k, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
+                  cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(k.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+  void* args[] = {const_cast<SsaRunParams*>(&p)};
+  err = cudaLaunchKernel(k.kernel, dim3(grid), dim3(k.block), args, smem_bytes, stream);
+  if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLaunchKernel: ") + cudaGetErrorString(err));
+  return REBOP_OK;
+}

@@ -1,0 +1,25 @@
+// jit.hpp -- run-time specialisation through NVRTC (K2 at run time).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include <string>
+#include <vector>
+
+#include "network.hpp"
+#include "ssa_params.h"
+
+struct RbJitKernel {
+  void* kernel = nullptr;  // cudaKernel_t
+  unsigned block = 128;
+  unsigned net_words = 0;
+};
+
+// Returns a compiled kernel for `net` on `device` (cached per process by source text).
+// REBOP_ERR_LIMIT when the network is too large to specialise, REBOP_ERR_NVRTC when NVRTC is
+// missing or the compilation fails (the message carries the log).
+int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out);
+// Source (and optionally the sm_100a cubin) of the specialised kernel; needs no GPU.
+int rb_jit_compile(const rebop_network& net, std::string* source, std::vector<char>* cubin);
+int rb_jit_launch(const RbJitKernel& k, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
+                  cudaStream_t stream);

@@ -1,0 +1,39 @@
+// ssa_params.h -- launch parameters of the ensemble kernels (host and device; no std includes,
+// so that NVRTC can compile it as is).
+#pragma once
+
+typedef unsigned long long rb_u64;
+typedef long long rb_i64;
+typedef unsigned int rb_u32;
+
+#define RB_FULL_MASK 0xffffffffu
+#define RB_ZIG_STRIDE 260  // doubles reserved per ziggurat table in shared memory
+
+// Status bits written to SsaRunParams::status.
+#define RB_STATUS_ITER_CAP 1u  // a trajectory hit max_iters before reaching its last grid point
+
+// Launch parameters (passed by value; lives in the constant bank).
+struct SsaRunParams {
+  int* x;                // [S][ldn] species counts, trajectory-contiguous
+  double* t;             // [ldn] current time of each trajectory
+  rb_u64* rng;           // [4][ldn] xoshiro256++ state
+  const rb_u64* seeds;   // [n_traj] or null; non-null => seed instead of loading rng
+  rb_u64 seed_base;      // used when seed_mode == 2: seed_n = seed_base + n
+  int* out;              // [(step-step_first)][n_save][ldn] samples, or null
+  rb_u64* events;        // [1] += applied reactions
+  rb_u32* status;        // [1] |= RB_STATUS_*
+  double tmax;
+  rb_u32 n_traj, ldn;
+  rb_u32 nb_steps;       // 0 => single target tmax (Gillespie::advance_until)
+  rb_u32 step_first, step_last;  // grid points handled by this launch (inclusive)
+  rb_u32 n_save;         // rows per sample
+  rb_u32 ring_depth;     // power of two, 1..32: grid points a warp can stage in shared memory
+  rb_u32 seed_mode;      // 0 load rng, 1 seeds[], 2 seed_base + n
+  rb_u32 max_iters;      // per-trajectory loop-iteration cap for this launch (0 = 2^32-1)
+  rb_u64 save_mask[2];   // specialised kernels: bit s set => species s is sampled
+  double k[64];          // specialised kernels: rate constants / parameters
+};
+
+// Shared memory (bytes) a launch needs: ziggurat tables + network tables + rings.
+#define RB_SSA_SMEM_BYTES(net_words, block, ring_depth, n_save) \
+  (4u * (4u * RB_ZIG_STRIDE + (net_words) + ((block) / 32u) * (ring_depth) * (n_save) * 32u))

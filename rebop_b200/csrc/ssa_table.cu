@@ -1,0 +1,150 @@
+// ssa_table.cu -- K1: table-driven direct-method kernel (any network, no JIT).
+//
+// Species counts live in shared memory (one column per thread, conflict-free),
+// rate constants / reactant terms / stoichiometry / expression byte-code sit in
+// __constant__ memory and are read warp-uniformly (every lane evaluates reaction
+// r at the same time, so each fetch is a broadcast).
+//
+// Replaces: Gillespie::advance_until + the pyo3 grid loop
+// (src/gillespie.rs:315-344, src/pyo3_gillespie.rs:197-208) with Rate::rate
+// (src/gillespie.rs:71-90), Expr::eval (src/expr.rs:24-38) and Jump::affect
+// (src/gillespie.rs:142-152) for LMASparse/Sparse forms, which the reference
+// pins as bit-identical to the dense forms (tests/test_rebop.py:55-65).
+#include <cuda_runtime.h>
+
+#include "rb_tables.h"
+#include "ssa_kernel.cuh"
+#include "ssa_table.h"
+
+__constant__ RbTables c_tab;
+
+struct RbTableNet {
+  static constexpr int BLOCK = RB_TABLE_BLOCK;
+  int* xs;  // this thread's column: species s at xs[s * BLOCK]
+
+  static __device__ __forceinline__ int smem_words(const SsaRunParams&) {
+    return c_tab.n_species * BLOCK;
+  }
+  __device__ __forceinline__ void init(const SsaRunParams&, int* smem, rb_u32 tid) { xs = smem + tid; }
+  __device__ __forceinline__ void load(const SsaRunParams& p, rb_u32 traj, bool valid) {
+    const int S = c_tab.n_species;
+    for (int s = 0; s < S; ++s) xs[s * BLOCK] = valid ? p.x[(size_t)s * p.ldn + traj] : 0;
+  }
+  __device__ __forceinline__ void store(const SsaRunParams& p, rb_u32 traj) {
+    const int S = c_tab.n_species;
+    for (int s = 0; s < S; ++s) p.x[(size_t)s * p.ldn + traj] = xs[s * BLOCK];
+  }
+
+  // Expr::eval on the post-order program of reaction r.
+  __device__ __noinline__ double eval_expr(int lo, int hi) const {
+    double stack[RB_EXPR_STACK];
+    int sp = 0;
+    for (int i = lo; i < hi; ++i) {
+      const int op = c_tab.op_code[i];
+      if (op == RB_OP_CONST) {
+        stack[sp++] = c_tab.op_val[i];
+      } else if (op == RB_OP_SPECIES) {
+        stack[sp++] = rb_i2d(xs[c_tab.op_idx[i] * BLOCK]);
+      } else if (op == RB_OP_NEG) {
+        stack[sp - 1] = -stack[sp - 1];
+      } else if (op == RB_OP_EXP) {
+        stack[sp - 1] = exp(stack[sp - 1]);
+      } else {
+        const double b = stack[--sp], a = stack[sp - 1];
+        double v;
+        switch (op) {
+          case RB_OP_ADD: v = __dadd_rn(a, b); break;
+          case RB_OP_SUB: v = __dsub_rn(a, b); break;
+          case RB_OP_MUL: v = __dmul_rn(a, b); break;
+          case RB_OP_DIV: v = __ddiv_rn(a, b); break;
+          case RB_OP_POW: v = pow(a, b); break;
+          case RB_OP_MAX: v = fmax(a, b); break;
+          case RB_OP_MIN: v = fmin(a, b); break;
+          default: v = __longlong_as_double(0x7ff8000000000000ll);
+        }
+        stack[sp - 1] = v;
+      }
+    }
+    return stack[0];
+  }
+
+  // Rate::rate for reaction r.
+  __device__ __forceinline__ double rate(int r) const {
+    const int e0 = c_tab.expr_ptr[r], e1 = c_tab.expr_ptr[r + 1];
+    if (e1 > e0) return eval_expr(e0, e1);
+    double acc = c_tab.k[r];
+    const int j1 = c_tab.term_ptr[r + 1];
+    for (int j = c_tab.term_ptr[r]; j < j1; ++j) {
+      const int n = xs[c_tab.term_idx[j] * BLOCK];
+      const int e = c_tab.term_exp[j];
+      if (e == 1) {
+        acc = __dmul_rn(acc, rb_i2d(n));
+      } else if (c_tab.arith == 0) {
+        // src/gillespie.rs:73-87: factors (n+1-e)..=n ascending, one f64 multiply each
+        for (int f = n + 1 - e; f <= n; ++f) acc = __dmul_rn(acc, rb_i2d(f));
+      } else {
+        // src/gillespie_macro.rs:133-146: wrapping integer falling factorial, one conversion
+        rb_u64 prod = (rb_u64)(rb_i64)n;
+        for (int i = 1; i < e; ++i) prod *= (rb_u64)(rb_i64)(n - i);
+        acc = __dmul_rn(acc, __ll2double_rn((rb_i64)prod));
+      }
+    }
+    return acc;
+  }
+
+  // make_cumrates (src/gillespie.rs:357-364); only the total is kept, fire() re-walks the sum.
+  __device__ __forceinline__ double propensities(const SsaRunParams&) const {
+    const int R = c_tab.n_reactions;
+    double total = 0.0;
+    for (int r = 0; r < R; ++r) total = __dadd_rn(total, rate(r));
+    return total;
+  }
+
+  __device__ __forceinline__ bool fire(const SsaRunParams&, double chosen) {
+    const int R = c_tab.n_reactions;
+    double cum = 0.0;
+    int i;
+    if (c_tab.arith == 0) {
+      // choose_cumrate_sum (src/gillespie.rs:402-407): the index is a count
+      i = 0;
+      for (int r = 0; r < R; ++r) {
+        cum = __dadd_rn(cum, rate(r));
+        i += (cum < chosen) ? 1 : 0;
+      }
+      if (i >= R) i = R - 1;  // unreachable for finite totals (src/gillespie.rs:339)
+    } else {
+      // _choice! (src/gillespie_macro.rs:150-171): first r with chosen < carry + r_r
+      i = R;
+      for (int r = 0; r < R; ++r) {
+        cum = __dadd_rn(cum, rate(r));
+        if (i == R && chosen < cum) i = r;
+      }
+      if (i == R) return false;
+    }
+    const int j1 = c_tab.jump_ptr[i + 1];
+    for (int j = c_tab.jump_ptr[i]; j < j1; ++j) xs[c_tab.jump_idx[j] * BLOCK] += c_tab.jump_diff[j];
+    return true;
+  }
+
+  __device__ __forceinline__ void record(const SsaRunParams& p, int* dst, rb_u32 stride) const {
+    for (rb_u32 j = 0; j < p.n_save; ++j) dst[(size_t)j * stride] = xs[c_tab.save_idx[j] * BLOCK];
+  }
+};
+
+__global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel(const __grid_constant__ SsaRunParams p) {
+  extern __shared__ __align__(16) int rb_smem[];
+  RbTableNet net;
+  rb_ssa_loop(net, p, rb_smem);
+}
+
+cudaError_t rb_table_launch(const RbTables* host_tables, const SsaRunParams& p, unsigned grid,
+                            size_t smem_bytes, cudaStream_t stream) {
+  cudaError_t err = cudaMemcpyToSymbolAsync(c_tab, host_tables, sizeof(RbTables), 0,
+                                            cudaMemcpyHostToDevice, stream);
+  if (err != cudaSuccess) return err;
+  err = cudaFuncSetAttribute(rb_ssa_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem_bytes);
+  if (err != cudaSuccess) return err;
+  rb_ssa_table_kernel<<<grid, RB_TABLE_BLOCK, smem_bytes, stream>>>(p);
+  return cudaGetLastError();
+}

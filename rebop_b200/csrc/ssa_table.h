@@ -1,0 +1,14 @@
+// ssa_table.h -- host entry of the table-driven kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#define RB_TABLE_BLOCK 128
+
+struct RbTables;
+struct SsaRunParams;
+
+// Uploads the tables to __constant__ memory on `stream`, then launches.  The host image must
+// stay valid until the copy has been issued (pageable memory: the call returns after staging).
+cudaError_t rb_table_launch(const RbTables* host_tables, const SsaRunParams& p, unsigned grid,
+                            size_t smem_bytes, cudaStream_t stream);

@@ -1,0 +1,152 @@
+"""Tier-1 parity: the CUDA path must reproduce the oracle's integer trajectories bit for bit.
+
+Every test calls through the C ABI (rebop_b200/_ffi.py) and compares with the CPU oracle on
+the same seeds.  Sizes are chosen so that the oracle finishes in seconds.
+"""
+import numpy as np
+import pytest
+
+from rebop_b200 import models
+from tests.helpers import numpy_seeds, oracle_network, run_product
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = {"table": 1, "nvrtc": 2}
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("name,n,tmax,nb_steps", [
+    ("sir", 4096, 250.0, 250),
+    ("dimers", 1024, 1.0, 4),
+    ("mm_lma", 2048, 100.0, 100),
+    ("vilar", 96, 20.0, 20),
+])
+def test_bit_exact_vs_oracle(gpu, ffi, oracle, kernel, arith, name, n, tmax, nb_steps):
+    model = models.MODELS[name]()
+    seeds = numpy_seeds(n, rng=7)
+    ref, ref_ev, ref_tot = oracle_network(oracle, model, arith).run_batch(model["x0"], seeds, tmax, nb_steps, threads=8)
+    out, ev, used = run_product(ffi, model, seeds, tmax, nb_steps, KERNELS[kernel], arith)
+    assert used == KERNELS[kernel]
+    assert out.shape == ref.shape
+    np.testing.assert_array_equal(out, ref)
+    assert ev == ref_tot
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+@pytest.mark.parametrize("n", [1, 31, 33, 127, 129, 1000])
+def test_ragged_sizes(gpu, ffi, oracle, kernel, n):
+    model = models.sir()
+    seeds = models.seeds_sequence(n, first=1000)
+    ref, _, tot = oracle_network(oracle, model).run_batch(model["x0"], seeds, 250.0, 50)
+    out, ev, _ = run_product(ffi, model, seeds, 250.0, 50, KERNELS[kernel])
+    np.testing.assert_array_equal(out, ref)
+    assert ev == tot
+
+
+def test_reference_golden_vector(gpu, ffi):
+    """tests/test_rebop.py:30-36: rng=42 => S=0, I=227, R=773 at t=250."""
+    seed = np.random.default_rng(42).integers(np.iinfo(np.uint64).max, dtype=np.uint64)
+    for kernel in KERNELS.values():
+        out, ev, _ = run_product(ffi, models.sir(), np.array([seed], dtype=np.uint64), 250.0, 250, kernel)
+        assert out[-1, :, 0].tolist() == [0, 227, 773]
+        assert out[0, :, 0].tolist() == [999, 1, 0]
+        assert ev == 1772
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+def test_seed_sequence_matches_explicit_seeds(gpu, ffi, kernel):
+    model = models.sir()
+    net = models.build_network(model)
+    n = 500
+    a = ffi.Batch(net, n, model["x0"], seeds=models.seeds_sequence(n, 12345), kernel=KERNELS[kernel])
+    b = ffi.Batch(net, n, model["x0"], seeds=None, seed_base=12345, kernel=KERNELS[kernel])
+    a.run_grid(100.0, 10)
+    b.run_grid(100.0, 10)
+    np.testing.assert_array_equal(a.samples(), b.samples())
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+def test_repeated_advance_until_continues_streams(gpu, ffi, oracle, kernel):
+    """Gillespie keeps its RNG between advance_until calls (src/lib.rs:129-133)."""
+    model = models.dimers()
+    n = 256
+    seeds = models.seeds_sequence(n)
+    net = models.build_network(model)
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds, kernel=KERNELS[kernel])
+    ref, _, tot = oracle_network(oracle, model).run_batch(model["x0"], seeds, 1.0, 4)
+    for i in range(5):
+        b.advance_until(1.0 * i / 4)
+        np.testing.assert_array_equal(b.species().T, ref[i])
+        np.testing.assert_array_equal(b.times(), np.full(n, 1.0 * i / 4))
+    assert b.events()[0] == tot
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+def test_var_names_subset(gpu, ffi, kernel):
+    """tests/test_rebop.py:68-89: saving a subset never changes the dynamics."""
+    model = models.sir()
+    seeds = models.seeds_sequence(300)
+    full, _, _ = run_product(ffi, model, seeds, 250.0, 25, KERNELS[kernel])
+    sub, _, _ = run_product(ffi, model, seeds, 250.0, 25, KERNELS[kernel], save_idx=[0, 2])
+    np.testing.assert_array_equal(sub, full[:, [0, 2], :])
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+def test_conservation_and_bounds(gpu, ffi, kernel):
+    """src/gillespie.rs:504-530, tests/test_rebop.py:15-27."""
+    model = models.sir()
+    out, _, _ = run_product(ffi, model, models.seeds_sequence(2000), 250.0, 250, KERNELS[kernel])
+    assert (out.sum(axis=1) == 1000).all()
+    assert (out >= 0).all() and (out[:, 0] <= 999).all()
+    model = models.dimers()
+    out, _, _ = run_product(ffi, model, models.seeds_sequence(200), 1.0, 1, KERNELS[kernel])
+    assert (out[-1, 0] == 1).all() and (out[-1, 2] > 1000).all() and (out[-1, 3] < 10000).all()
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+def test_nan_rate_freezes(gpu, ffi, kernel):
+    """src/gillespie_macro.rs:224-238: a NaN rate constant => no reaction, t = tmax."""
+    net = ffi.Network(1, 1)
+    net.add_reaction_lma_sparse(10.0, [], [1])
+    net.add_reaction_lma_sparse(float("nan"), [(0, 1)], [-1])
+    b = ffi.Batch(net, 64, [0], seeds=models.seeds_sequence(64), kernel=KERNELS[kernel])
+    b.advance_until(100.0)
+    assert (b.species() == 0).all()
+    assert (b.times() == 100.0).all()
+    assert b.events()[0] == 0
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+def test_no_reactions(gpu, ffi, kernel):
+    """src/gillespie_macro.rs:239-253."""
+    net = ffi.Network(3, 0)
+    b = ffi.Batch(net, 40, [42, 1337, 0], seeds=models.seeds_sequence(40), kernel=KERNELS[kernel])
+    b.run_grid(1e20, 3)
+    out = b.samples()
+    assert (out[:, 0] == 42).all() and (out[:, 1] == 1337).all() and (out[:, 2] == 0).all()
+    assert (b.times() == 1e20).all()
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+def test_sample_sums(gpu, ffi, kernel):
+    model = models.sir()
+    n = 3001
+    net = models.build_network(model)
+    b = ffi.Batch(net, n, model["x0"], seeds=models.seeds_sequence(n), kernel=KERNELS[kernel])
+    b.run_grid(250.0, 20)
+    out = b.samples().astype(np.int64)
+    s1, s2 = b.sample_sums()
+    np.testing.assert_array_equal(s1.reshape(21, 3), out.sum(axis=2))
+    np.testing.assert_array_equal(s2.reshape(21, 3).astype(np.int64), (out * out).sum(axis=2))
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+def test_iteration_cap_is_reported(gpu, ffi, kernel):
+    model = models.sir()
+    net = models.build_network(model)
+    b = ffi.Batch(net, 64, model["x0"], seeds=models.seeds_sequence(64), kernel=KERNELS[kernel])
+    b.set_max_iters(10)
+    with pytest.raises(ffi.RebopError) as e:
+        b.run_grid(250.0, 250)
+    assert e.value.status == ffi.ERR_ITER_CAP
