@@ -1,0 +1,397 @@
+#!/usr/bin/env python3
+"""Headline benchmark: SSA reaction events/s for the Vilar oscillator ensemble.
+
+Workload (BASELINE.json configs[3]): Vilar circadian oscillator (9 species, 16 reactions,
+benchmarks/benches/vilar/vilar.rs:6-46 of the reference), t = 0..200 sampled every 1 time unit
+(201 x 9 samples per trajectory), 10^7 trajectories sharded over 8 GPUs = 1.25e6 per GPU, weak
+scaling (every GPU always simulates 1.25e6 trajectories; trajectory n uses seed n).
+
+A "step" is one pass of the hot path over one shard: every trajectory of the shard from t = 0 to
+t = 200 in ONE kernel launch, samples left in HBM as int32 [step][species][trajectory].
+
+  value  device-resident: seeds derived on the device (seed = base + n), samples stay in HBM.
+  e2e    the C-ABI call a host makes, with HOST buffers: per step the per-trajectory seeds and x0 are
+         copied from pinned host memory, the kernel runs, and the full sample tensor is copied back
+         into a pinned host buffer, all inside the timed region.
+  roofline  the kernel is FP64/INT issue bound, not HBM bound: `achieved` = events x F / kernel time
+         with F = O + 2R + 9 = 60 non-fused FP64 operations per event, `peak` = the
+         non-fused FP64 issue rate measured on this GPU in this run; the `hbm` sub-object reports
+         the sample stores against MEASURED_PEAKS.json.
+  cpu_baseline  the oracle's define_system!-style straight-line Vilar code on all host cores, on a
+         bounded sample of the same workload (N=1, rank 0 only).
+
+`--impl reference` times the reference's CPU algorithm (the oracle port; the Rust crate cannot be
+compiled in this image) on the host cores and prints the same JSON line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ssa_reaction_events_per_sec"
+UNIT = "events/s"
+TRAJ_PER_GPU = 1_250_000  # 10^7 over 8 GPUs
+FP64_OPS_PER_EVENT = {"vilar": 60, "sir": 16, "dimers": 25, "mm_lma": 18}  # F = O + 2R + 9
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"{args.model} ensemble, define_system! arithmetic, tmax={args.tmax:g}, nb_steps={args.nb_steps}, "
+                    f"{args.traj_per_gpu} trajectories per GPU ({args.traj_per_gpu * n_gpus} total), all species saved",
+        "trajectories_per_gpu": args.traj_per_gpu,
+        "trajectories_total": args.traj_per_gpu * n_gpus,
+        "tmax": args.tmax,
+        "nb_steps": args.nb_steps,
+        "sharding": f"trajectories x{n_gpus}, no data-path collective",
+        "l2": "sample tensor written per step exceeds L2 (%.2f GB); inputs are seeds only"
+              % (args.traj_per_gpu * (args.nb_steps + 1) * args.n_species * 4 / 1e9),
+    }
+
+
+# --------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_sample(model, n_traj, tmax, nb_steps, threads, seed_first=0):
+    """Oracle (define_system! form) on `threads` host threads -> (events, seconds)."""
+    from oracle import oracle as O  # checker / CPU baseline only
+
+    seeds = np.arange(seed_first, seed_first + n_traj, dtype=np.uint64)
+    t0 = time.perf_counter()
+    _, _, events = O.run_batch_macro(model["name"], model["params"], model["x0"], seeds, tmax, nb_steps,
+                                     threads=threads, want_out=True, want_events=False)
+    return events, time.perf_counter() - t0
+
+
+def run_reference(args, model):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    per_step = max(cores, args.ref_traj_per_core * cores)
+    for i in range(args.warmup):
+        cpu_sample(model, per_step, args.tmax, args.nb_steps, cores, seed_first=i * per_step)
+    events = 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ev, _ = cpu_sample(model, per_step, args.tmax, args.nb_steps, cores, seed_first=(args.warmup + i) * per_step)
+        events += ev
+    dt = time.perf_counter() - t0
+    value = events / dt
+    sample = f"{per_step} trajectories per step ({args.ref_traj_per_core} per core) of the same workload"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "trajectories_per_s": per_step * args.steps / dt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle port of the reference's define_system! code path (the Rust crate cannot be built here: no cargo/rustc)",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fh = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = fh.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=fh, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for raw in open(self.path):
+            f = [c.strip() for c in raw.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_gpu(args, model):
+    import torch
+    import torch.distributed as dist
+
+    from rebop_b200 import _ffi, models
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if _ffi.device_count() <= local:
+        raise SystemExit("bench.py needs a CUDA device per rank (rebop_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n = args.traj_per_gpu
+    S = len(model["species"])
+    nb = args.nb_steps
+    net = models.build_network(model, _ffi.ARITH_MACRO)
+    kernel = {"auto": _ffi.KERNEL_AUTO, "table": _ffi.KERNEL_TABLE, "nvrtc": _ffi.KERNEL_NVRTC}[args.kernel]
+
+    def shard_base(step_index):  # distinct trajectories every step and every rank
+        return (step_index * world + rank) * n
+
+    batch = _ffi.Batch(net, n, model["x0"], seeds=None, seed_base=shard_base(0), device=local, kernel=kernel)
+    stream = torch.cuda.ExternalStream(batch.stream, device=torch.device("cuda", local))
+
+    def device_step(i):
+        batch.set_species(model["x0"])
+        batch.set_time(0.0)
+        batch.seed(None, shard_base(i))
+        batch.run_grid(args.tmax, nb)
+        return batch.events()[1], batch.last_kernel_ms
+
+    # ---- value: device-resident -------------------------------------------------------
+    for i in range(args.warmup):
+        device_step(i)
+    sampler = ClockSampler(local)
+    launches0 = _ffi.kernel_launches()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    events = 0
+    kernel_ms = 0.0
+    w0 = time.perf_counter()
+    for i in range(args.steps):
+        ev, ms = device_step(args.warmup + i)
+        events += ev
+        kernel_ms += ms
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - w0
+    clocks = sampler.stop()
+    launches = _ffi.kernel_launches() - launches0
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    total_events = sum_over_ranks(float(events))
+    value = total_events / (dev_ms * 1e-3)
+    kernel_used = batch.kernel_used
+
+    # ---- ensemble statistics: K4 sums, all-reduced over the GPUs with NCCL (north_star's only collective)
+    stats_ms = None
+    t0 = time.perf_counter()
+    dptr, rows = batch.sample_sums_device()
+    batch.synchronize()
+    if world > 1:
+        holder = type("Sums", (), {"__cuda_array_interface__": {
+            "shape": (2 * rows,), "typestr": "<i8", "data": (dptr, False), "version": 3}})()
+        sums = torch.as_tensor(holder, device=torch.device("cuda", local))
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        sums_host = sums.cpu().numpy()
+    else:
+        s1, s2 = batch.sample_sums()
+        sums_host = np.concatenate([s1, s2.astype(np.int64)])
+    stats_ms = (time.perf_counter() - t0) * 1e3
+    n_total = n * world
+    mean_last = (sums_host[:rows].reshape(nb + 1, S)[-1] / n_total).tolist()
+
+    # ---- e2e: host buffers through the C ABI ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_out = _ffi.PinnedBuffer((nb + 1, S, n), np.int32)
+        host_seeds = _ffi.PinnedBuffer((n,), np.uint64)
+        x0 = np.asarray(model["x0"], dtype=np.int64)
+
+        def e2e_step(i):
+            host_seeds.array[:] = np.arange(shard_base(i), shard_base(i) + n, dtype=np.uint64)
+            batch.set_species(x0)
+            batch.set_time(0.0)
+            batch.seed(host_seeds.array)
+            batch.run_grid(args.tmax, nb, host_out=host_out.array)
+            return batch.events()[1]
+
+        for i in range(args.warmup):
+            e2e_step(i)
+        barrier()
+        w0 = time.perf_counter()
+        e2e_events = 0
+        for i in range(args.steps):
+            e2e_events += e2e_step(args.warmup + i)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - w0)
+        e2e_total = sum_over_ranks(float(e2e_events))
+        checksum = int(host_out.array[-1].astype(np.int64).sum())
+        e2e = {"value": e2e_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 8 + S * 4),
+               "d2h_bytes_per_step": int((nb + 1) * S * n * 4), "ms_per_step": e2e_s / args.steps * 1e3,
+               "trajectories_per_s": n * world * args.steps / e2e_s, "last_row_checksum": checksum,
+               "api": "rebop_batch_seed + rebop_batch_run_grid(host_out) with pinned host buffers"}
+        host_out.close()
+        host_seeds.close()
+
+    # ---- roofline of the dominant kernel (this rank) ---------------------------------------
+    fp64_peak, fp64_mhz = _ffi.measure_fp64_rate(local)
+    F = FP64_OPS_PER_EVENT.get(model["name"])
+    ms_per_launch = kernel_ms / args.steps
+    ev_per_launch = events / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    sample_bytes = (nb + 1) * S * n * 4 + n * (S * 4 + 8 + 32) * 2
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tr.get("model") == model["name"] and tr.get("nb_steps") == nb:
+            traffic = tr["dram_bytes_per_trajectory"] * n
+    except (OSError, KeyError, ValueError):
+        pass
+    achieved = ev_per_launch * F / (ms_per_launch * 1e-3) / 1e9 if F else None
+    roofline = {
+        "kernel": "rb_ssa_jit" if kernel_used == _ffi.KERNEL_NVRTC else "rb_ssa_table_kernel",
+        "bound": "fp64_issue", "achieved": achieved, "peak": fp64_peak / 1e9, "unit": "GFLOP/s (non-fused f64 ops)",
+        "frac": achieved / (fp64_peak / 1e9) if achieved else None,
+        "peak_source": "measured in this run: independent DADD/DMUL chains on all SMs at %.0f MHz" % fp64_mhz,
+        "ops_per_event": F, "events_per_launch": ev_per_launch, "ms_per_launch": ms_per_launch,
+        "traffic": traffic,
+        "hbm": {"bound": "hbm", "achieved": sample_bytes / (ms_per_launch * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": sample_bytes / (ms_per_launch * 1e-3) / 1e9 / hbm_peak, "bytes_per_launch": sample_bytes,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+    }
+
+    # ---- CPU baseline (rank 0, N = 1) -------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = host_cores()
+        n_cpu = max(cores, args.cpu_traj_per_core * cores)
+        cpu_sample(model, cores, args.tmax, args.nb_steps, cores)  # warm the threads and caches
+        ev, dt = cpu_sample(model, n_cpu, args.tmax, args.nb_steps, cores, seed_first=10**9)
+        cpu = {"value": ev / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} trajectories of the same workload in {dt:.1f} s (oracle, define_system! form, {cores} threads)"}
+
+    batch.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "trajectories_per_s": n * world * args.steps / (dev_ms * 1e-3),
+            "events_per_step": total_events / args.steps,
+            "wall_ms_per_step": wall / args.steps * 1e3,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "kernel": roofline["kernel"], "roofline": roofline, "cpu_baseline": cpu,
+            "ensemble_stats": {"ms": stats_ms, "collective": "nccl all_reduce(int64 sum)" if world > 1 else "none (1 GPU)",
+                               "mean_at_tmax": dict(zip(model["species"], mean_last))},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="vilar")
+    ap.add_argument("--traj-per-gpu", type=int, default=TRAJ_PER_GPU)
+    ap.add_argument("--tmax", type=float, default=None)
+    ap.add_argument("--nb-steps", type=int, default=None)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "table", "nvrtc"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-traj-per-core", type=int, default=96, help="cpu_baseline sample size per host core")
+    ap.add_argument("--ref-traj-per-core", type=int, default=16, help="--impl reference: trajectories per core per step")
+    args = ap.parse_args()
+
+    from rebop_b200 import models
+    model = models.MODELS[args.model]()
+    args.tmax = model["tmax"] if args.tmax is None else args.tmax
+    args.nb_steps = model["nb_steps"] if args.nb_steps is None else args.nb_steps
+    args.n_species = len(model["species"])
+
+    if args.impl == "reference":
+        return run_reference(args, model)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu(args, model)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

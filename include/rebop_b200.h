@@ -139,7 +139,8 @@ int rebop_batch_set_species(rebop_batch* b, const int64_t* species, int per_traj
 /* Gillespie::advance_until (src/gillespie.rs:315-344) on every trajectory. */
 int rebop_batch_advance_until(rebop_batch* b, double tmax);
 /* The pyo3 grid loop (src/pyo3_gillespie.rs:197-208): for i in 0..=nb_steps
- * { advance_until(tmax*i/nb_steps); record species[save_idx] }.  save_idx NULL = all species.
+ * { advance_until(tmax*i/nb_steps); record species[save_idx] }.  save_idx: strictly increasing
+ * species indices, or NULL for all species.
  * Samples stay on the device as int32 [nb_steps+1][n_save][ld] (ld >= n_traj).
  * host_out (optional): caller buffer of (nb_steps+1)*n_save*n_traj int32 that receives them
  * densely as [step][save][trajectory]. */
@@ -163,8 +164,24 @@ int rebop_batch_last_kernel_ms(rebop_batch* b, float* ms);
 int rebop_batch_size(const rebop_batch* b, size_t* n_traj);
 /* Block until the device has finished the batch's queued work. */
 int rebop_batch_synchronize(rebop_batch* b);
+/* The CUDA stream (cudaStream_t / CUstream) every launch and copy of this batch is issued on, so
+ * that a host framework can order its own work (events, collectives) against it. */
+int rebop_batch_get_stream(const rebop_batch* b, void** stream);
+/* Issue this batch's work on a caller-owned stream instead (NULL restores the batch's own). */
+int rebop_batch_set_stream(rebop_batch* b, void* stream);
+
+/* ---- host memory ---- */
+
+/* Page-locked host memory for result buffers (device-to-host copies into it run at full PCIe
+ * rate and asynchronously).  Stands in for the Vec the reference returns
+ * (src/pyo3_gillespie.rs:224-237); the caller frees it with rebop_b200_host_free. */
+int rebop_b200_host_alloc(size_t bytes, void** out);
+int rebop_b200_host_free(void* p);
 
 /* ---- measurement helpers ---- */
+
+/* Number of kernels this library has launched in the calling process so far (all batches). */
+uint64_t rebop_b200_kernel_launches(void);
 
 /* Sustained non-fused FP64 issue rate of `device` in operations per second (independent
  * DADD/DMUL chains, all SMs) -- the denominator of the per-event FP64 roofline. */

@@ -91,6 +91,11 @@ SIGNATURES = {
     "rebop_batch_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rebop_batch_size": (C.c_int, [_vp, _szp]),
     "rebop_batch_synchronize": (C.c_int, [_vp]),
+    "rebop_batch_get_stream": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
+    "rebop_batch_set_stream": (C.c_int, [_vp, _vp]),
+    "rebop_b200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rebop_b200_host_free": (C.c_int, [_vp]),
+    "rebop_b200_kernel_launches": (C.c_uint64, []),
     "rebop_b200_measure_fp64_rate": (C.c_int, [C.c_int, _f64p, _f64p]),
 }
 
@@ -355,6 +360,43 @@ class Batch:
 
     def synchronize(self) -> None:
         check(lib.rebop_batch_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t the batch issues its work on (as an integer handle)."""
+        p = C.c_void_p()
+        check(lib.rebop_batch_get_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def set_stream(self, stream: int | None) -> None:
+        check(lib.rebop_batch_set_stream(self._h, C.c_void_p(stream or None)))
+
+
+def kernel_launches() -> int:
+    return int(lib.rebop_b200_kernel_launches())
+
+
+class PinnedBuffer:
+    """Page-locked host array (rebop_b200_host_alloc) exposed as a numpy view."""
+
+    def __init__(self, shape, dtype=np.int32):
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(lib.rebop_b200_host_alloc(nbytes, C.byref(p)))
+        self._p = p
+        buf = (C.c_char * max(1, nbytes)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=nbytes // self.dtype.itemsize).reshape(self.shape)
+
+    def close(self) -> None:
+        if getattr(self, "_p", None):
+            self.array = None
+            lib.rebop_b200_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        self.close()
 
 
 def measure_fp64_rate(device: int = 0):

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -24,6 +25,9 @@
     if (err__ != cudaSuccess)                                                                  \
       return rb_fail(REBOP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));   \
   } while (0)
+
+static std::atomic<uint64_t> g_kernel_launches{0};
+extern "C" uint64_t rebop_b200_kernel_launches(void) { return g_kernel_launches.load(); }
 
 struct rebop_batch {
   rebop_network net;
@@ -42,7 +46,8 @@ struct rebop_batch {
   rb_u64* d_counters = nullptr;  // [0] events, [1] status (low 32 bits)
   rb_i64* d_sums = nullptr;
   size_t sums_capacity = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream work is issued on
+  cudaStream_t own_stream = nullptr;  // created with the batch; `stream` may point elsewhere
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint64_t events_total = 0, events_last = 0;
   int kernel_pref = REBOP_KERNEL_AUTO, kernel_used = REBOP_KERNEL_AUTO;
@@ -167,6 +172,7 @@ static int upload_x0(rebop_batch* b, const int64_t* x0, int per_traj) {
     rb_fill_state_kernel<<<(unsigned)((b->ldn + 255) / 256), 256, 0, b->stream>>>(
         b->d_x, b->d_t, d_x0, S, (unsigned)b->ldn, (unsigned)b->n, 0.0, 1, 0);
     RB_CUDA(cudaGetLastError());
+    ++g_kernel_launches;
     RB_CUDA(cudaStreamSynchronize(b->stream));  // h goes out of scope
     RB_CUDA(cudaFreeAsync(d_x0, b->stream));
   } else {
@@ -199,11 +205,12 @@ extern "C" void rebop_batch_destroy(rebop_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
+  if (b->own_stream && b->own_stream != b->stream) cudaStreamSynchronize(b->own_stream);
   cudaFree(b->d_x); cudaFree(b->d_t); cudaFree(b->d_rng); cudaFree(b->d_seeds);
   cudaFree(b->d_out); cudaFree(b->d_counters); cudaFree(b->d_sums);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
-  if (b->stream) cudaStreamDestroy(b->stream);
+  if (b->own_stream) cudaStreamDestroy(b->own_stream);
   delete b;
 }
 
@@ -234,7 +241,8 @@ extern "C" int rebop_batch_create(const rebop_network* net, int device, size_t n
   const size_t S = net->n_species ? net->n_species : 1;
   RB_CREATE_CUDA(cudaDeviceGetAttribute(&b->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   RB_CREATE_CUDA(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
-  RB_CREATE_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  RB_CREATE_CUDA(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+  b->stream = b->own_stream;
   RB_CREATE_CUDA(cudaEventCreate(&b->ev0));
   RB_CREATE_CUDA(cudaEventCreate(&b->ev1));
   RB_CREATE_CUDA(cudaMalloc(&b->d_x, S * b->ldn * sizeof(int)));
@@ -283,6 +291,32 @@ extern "C" int rebop_batch_synchronize(rebop_batch* b) {
   return REBOP_OK;
 }
 
+extern "C" int rebop_batch_get_stream(const rebop_batch* b, void** stream) {
+  if (!b || !stream) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  *stream = b->stream;
+  return REBOP_OK;
+}
+extern "C" int rebop_batch_set_stream(rebop_batch* b, void* stream) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  RB_CUDA(cudaStreamSynchronize(b->stream));  // hand over with nothing in flight on the old stream
+  b->stream = stream ? static_cast<cudaStream_t>(stream) : b->own_stream;
+  return REBOP_OK;
+}
+
+extern "C" int rebop_b200_host_alloc(size_t bytes, void** out) {
+  if (!out) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (rebop_b200_device_count() == 0)
+    return rb_fail(REBOP_ERR_CUDA, "no CUDA device available (page-locked memory needs a driver)");
+  RB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return REBOP_OK;
+}
+extern "C" int rebop_b200_host_free(void* p) {
+  if (p) RB_CUDA(cudaFreeHost(p));
+  return REBOP_OK;
+}
+
 extern "C" int rebop_batch_seed(rebop_batch* b, const uint64_t* seeds, uint64_t seed_base) {
   if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   RB_CUDA(cudaSetDevice(b->device));
@@ -303,6 +337,7 @@ extern "C" int rebop_batch_set_time(rebop_batch* b, double t) {
   rb_fill_state_kernel<<<(unsigned)((b->ldn + 255) / 256), 256, 0, b->stream>>>(
       b->d_x, b->d_t, nullptr, 0, (unsigned)b->ldn, (unsigned)b->n, t, 0, 1);
   RB_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
   return REBOP_OK;
 }
 
@@ -415,6 +450,7 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     b->kernel_used = REBOP_KERNEL_TABLE;
   }
   RB_CUDA(cudaEventRecord(b->ev1, b->stream));
+  ++g_kernel_launches;
 
   rb_u64 counters[2] = {0, 0};
   RB_CUDA(cudaMemcpyAsync(counters, b->d_counters, sizeof counters, cudaMemcpyDeviceToHost, b->stream));
@@ -447,8 +483,11 @@ extern "C" int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_ste
     save_idx = all.data();
     n_save = S;
   }
-  for (uint32_t j = 0; j < n_save; ++j)
+  for (uint32_t j = 0; j < n_save; ++j) {
     if (save_idx[j] >= S) return rb_fail(REBOP_ERR_OUT_OF_RANGE, "save_idx refers to a species index out of range");
+    if (j > 0 && save_idx[j] <= save_idx[j - 1])
+      return rb_fail(REBOP_ERR_INVALID, "save_idx must be strictly increasing");
+  }
   const size_t rows = (size_t)(nb_steps + 1) * n_save;
   const size_t need = std::max<size_t>(1, rows * b->ldn);
   if (need > b->out_capacity) {
@@ -514,6 +553,7 @@ extern "C" int rebop_batch_sample_sums_device(rebop_batch* b, const int64_t** de
   dim3 grid(per_row, rows);
   rb_row_sums_kernel<<<grid, 256, 0, b->stream>>>(b->d_out, (unsigned)b->n, (unsigned)b->ldn, b->d_sums, rows);
   RB_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
   if (dev_ptr) *dev_ptr = reinterpret_cast<const int64_t*>(b->d_sums);
   if (n_rows) *n_rows = rows;
   return REBOP_OK;
@@ -562,6 +602,7 @@ extern "C" int rebop_b200_measure_fp64_rate(int device, double* ops_per_second, 
   for (int rep = 0; rep < 5; ++rep) {  // first pass warms up
     RB_CUDA(cudaEventRecord(e0));
     rb_fp64_probe_kernel<<<blocks, threads>>>(sink, iters, clocks);
+    ++g_kernel_launches;
     RB_CUDA(cudaEventRecord(e1));
     RB_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;

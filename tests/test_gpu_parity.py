@@ -150,3 +150,49 @@ def test_iteration_cap_is_reported(gpu, ffi, kernel):
     with pytest.raises(ffi.RebopError) as e:
         b.run_grid(250.0, 250)
     assert e.value.status == ffi.ERR_ITER_CAP
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+def test_golden_fixtures(gpu, ffi, kernel):
+    """Committed fixtures (tests/golden/, full-length runs incl. Vilar to t=200 and the reference's
+    rng=42 vector): final states, per-run event totals and a checksum over every sample."""
+    import json
+    import os
+
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    files = sorted(f for f in os.listdir(gdir) if f.endswith(".json"))
+    assert files
+    for f in files:
+        g = json.load(open(os.path.join(gdir, f)))
+        model = models.MODELS[g["model"]]()
+        seeds = np.array(g["seeds"], dtype=np.uint64)
+        out, ev, _ = run_product(ffi, model, seeds, g["tmax"], g["nb_steps"], KERNELS[kernel], g["arith"])
+        assert out[-1].T.tolist() == g["final"], f
+        assert ev == sum(g["events"]), f
+        assert int(out.astype(np.int64).sum()) == g["checksum"], f
+
+
+def test_full_size_properties(gpu, ffi):
+    """BASELINE-size run (SIR, 10^6 trajectories x 251 samples, config C1) checked through properties
+    that do not need the oracle: conservation, monotonicity, row 0, exact K4 sums, and equality of
+    the two kernels on a strided subsample."""
+    model = models.sir()
+    n = 1_000_000
+    net = models.build_network(model)
+    b = ffi.Batch(net, n, model["x0"], seeds=None, seed_base=0, kernel=KERNELS["nvrtc"])
+    b.run_grid(250.0, 250)
+    out = b.samples()
+    s1, s2 = b.sample_sums()
+    ev = b.events()[0]
+    b.close()
+    assert out.shape == (251, 3, n)
+    assert (out.sum(axis=1) == 1000).all()
+    assert (out[0, 0] == 999).all() and (out[0, 1] == 1).all() and (out[0, 2] == 0).all()
+    assert (np.diff(out[:, 0, ::97], axis=0) <= 0).all() and (np.diff(out[:, 2, ::97], axis=0) >= 0).all()
+    np.testing.assert_array_equal(s1.reshape(251, 3), out.sum(axis=2, dtype=np.int64))
+    assert 1.55e9 < ev < 1.70e9  # SURVEY.md 8(d): 1622 events per trajectory on average
+    # every event moves exactly one individual: events = (S0 - S_end) + R_end summed over trajectories
+    assert ev == int((999 - out[-1, 0].astype(np.int64)).sum() + out[-1, 2].astype(np.int64).sum())
+    sub = np.arange(0, n, 4001, dtype=np.uint64)
+    t, _, _ = run_product(ffi, model, sub, 250.0, 250, KERNELS["table"])
+    np.testing.assert_array_equal(t, out[:, :, ::4001])
