@@ -251,17 +251,10 @@ def run_gpu(args, model):
     # ---- ensemble statistics: K4 sums, all-reduced over the GPUs with NCCL (north_star's only collective)
     stats_ms = None
     t0 = time.perf_counter()
-    dptr, rows = batch.sample_sums_device()
-    batch.synchronize()
-    if world > 1:
-        holder = type("Sums", (), {"__cuda_array_interface__": {
-            "shape": (2 * rows,), "typestr": "<i8", "data": (dptr, False), "version": 3}})()
-        sums = torch.as_tensor(holder, device=torch.device("cuda", local))
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        sums_host = sums.cpu().numpy()
-    else:
-        s1, s2 = batch.sample_sums()
-        sums_host = np.concatenate([s1, s2.astype(np.int64)])
+    from rebop_b200 import ensemble
+    sums, rows = ensemble.device_sums_as_tensor(batch, local)  # K4 on this GPU's shard
+    ensemble.allreduce_sums(sums)                               # NCCL, int64 sum (no-op at N=1)
+    sums_host = sums.cpu().numpy()
     stats_ms = (time.perf_counter() - t0) * 1e3
     n_total = n * world
     mean_last = (sums_host[:rows].reshape(nb + 1, S)[-1] / n_total).tolist()
@@ -314,8 +307,8 @@ def run_gpu(args, model):
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tr.get("model") == model["name"] and tr.get("nb_steps") == nb:
-            traffic = tr["dram_bytes_per_trajectory"] * n
+        if tr.get("model") == model["name"]:  # measured per (trajectory, sample row); scaled to this launch
+            traffic = tr["dram_bytes_per_trajectory_row"] * n * (nb + 1)
     except (OSError, KeyError, ValueError):
         pass
     achieved = ev_per_launch * F / (ms_per_launch * 1e-3) / 1e9 if F else None

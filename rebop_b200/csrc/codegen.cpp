@@ -8,6 +8,7 @@
 #include "codegen.hpp"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -53,7 +54,67 @@ std::string emit_expr(const std::vector<rebop_expr_op>& prog) {
   return st.empty() ? "0.0" : st.back();
 }
 
+// Cumulative rates are non-decreasing for every reachable state when all reactions are mass-action
+// with a non-negative constant and no reaction can drive a count negative (every species a reaction
+// consumes is a reactant of at least that order, so the propensity is 0 before the count would go
+// below 0).  The initial state must be non-negative too, which the engine checks per batch.
+bool network_is_monotone(const rebop_network& net) {
+  for (const RbReaction& rx : net.rx) {
+    if (rx.is_expr) return false;
+    if (!(rx.k >= 0.0)) return false;  // also rejects NaN
+    for (size_t s = 0; s < rx.diff.size(); ++s) {
+      if (rx.diff[s] >= 0) continue;
+      int64_t order = 0;
+      for (size_t j = 0; j < rx.term_idx.size(); ++j)
+        if (rx.term_idx[j] == s) order += rx.term_exp[j];
+      if (order < -rx.diff[s]) return false;
+    }
+  }
+  return true;
+}
+
+// Branch-free binary search over the register-resident cumulative rates c[0..R-2] (c[R-1] and the
+// padding up to a power of two count as +inf, which is what clamping the index to R-1 means).
+// `probe(j)` is the source text of the predicate "move right past c[j]".
+struct BinarySearchEmitter {
+  std::ostringstream& o;
+  int R;
+  std::string (*probe)(const std::string& value);
+  // emits code selecting c[lo_index(bits)] for the current level; returns the expression
+  std::string select(int level, int prefix, int depth, int half) const {
+    // candidates at this level: prefix (already decided high bits) -> index prefix + half - 1
+    if (depth == level) {
+      const int j = prefix + half - 1;
+      return j <= R - 2 ? "c[" + std::to_string(j) + "]" : std::string();
+    }
+    const int bit = half << (level - depth);  // weight of decision `depth`
+    const std::string hi = select(level, prefix + bit, depth + 1, half);
+    const std::string lo = select(level, prefix, depth + 1, half);
+    if (hi.empty()) return lo.empty() ? std::string() : "(q" + std::to_string(depth) + " ? RB_INF : " + lo + ")";
+    return "(q" + std::to_string(depth) + " ? " + hi + " : " + lo + ")";
+  }
+};
+
 }  // namespace
+
+bool rb_codegen_monotone(const rebop_network& net) { return network_is_monotone(net); }
+
+RbCodegenOptions rb_codegen_default_options() {
+  RbCodegenOptions opt;
+  if (const char* env = std::getenv("REBOP_B200_CODEGEN")) {
+    const std::string e(env);
+    auto get = [&](const char* key, int def) {
+      const size_t pos = e.find(std::string(key) + "=");
+      return pos == std::string::npos ? def : std::atoi(e.c_str() + pos + std::strlen(key) + 1);
+    };
+    opt.conv = get("conv", opt.conv);
+    opt.select = get("select", opt.select);
+    opt.bake = get("bake", opt.bake);
+    opt.block = get("block", opt.block);
+    opt.min_ctas = get("minctas", opt.min_ctas);
+  }
+  return opt;
+}
 
 bool rb_codegen_supported(const rebop_network& net, std::string* why) {
   if (net.n_species > RB_GEN_MAX_SPECIES) {

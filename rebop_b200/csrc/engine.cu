@@ -52,6 +52,7 @@ struct rebop_batch {
   uint64_t events_total = 0, events_last = 0;
   int kernel_pref = REBOP_KERNEL_AUTO, kernel_used = REBOP_KERNEL_AUTO;
   uint32_t max_iters = 0;
+  uint32_t slow_batch = 4;  // parked ziggurat slow-path lanes per warp before they are served
   float last_ms = 0.f;
   RbTables tables;
   bool tables_ok = false;
@@ -373,7 +374,7 @@ static unsigned pow2_floor(unsigned v) {
 static unsigned choose_ring_depth(const rebop_batch* b, unsigned block, unsigned net_words, unsigned n_save,
                                   unsigned n_points, unsigned ctas_per_sm) {
   if (n_save == 0) return 1;
-  const size_t fixed = 4u * (4u * RB_ZIG_STRIDE + net_words);
+  const size_t fixed = 4u * (RB_ZIG_WORDS + net_words);
   const size_t per_depth = (size_t)(block / 32u) * n_save * 32u * 4u;
   const size_t budget = (size_t)b->max_smem_optin / (ctas_per_sm ? ctas_per_sm : 1);
   unsigned depth = 1;
@@ -406,6 +407,7 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   p.n_save = d_out ? n_save : 0;
   p.seed_mode = b->seed_mode;
   p.max_iters = b->max_iters;
+  p.slow_batch = b->slow_batch;
   const unsigned n_points = step_last - step_first + 1;
 
   RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(rb_u64), b->stream));

@@ -7,7 +7,10 @@
 
 #include <dlfcn.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -80,8 +83,25 @@ std::map<std::pair<int, std::string>, CacheEntry> g_cache;
 static int compile_to_cubin(const std::string& src, std::vector<char>* cubin) {
   Nvrtc& n = nvrtc();
   if (!n.error.empty()) return rb_fail(REBOP_ERR_NVRTC, "NVRTC unavailable: " + n.error);
+  // REBOP_B200_JIT_DUMP=<dir>: keep the generated source (and the headers it includes) on disk and
+  // compile it under that path, so that profilers (ncu --import-source) can show it.
+  std::string prog_name = "rb_ssa_jit.cu";
+  if (const char* dir = std::getenv("REBOP_B200_JIT_DUMP")) {
+    char tag[32];
+    std::snprintf(tag, sizeof tag, "%016zx", std::hash<std::string>{}(src));
+    const std::string base = std::string(dir) + "/";
+    auto dump = [](const std::string& path, const char* text) {
+      if (FILE* fh = std::fopen(path.c_str(), "w")) {
+        std::fputs(text, fh);
+        std::fclose(fh);
+      }
+    };
+    prog_name = base + "rb_ssa_jit_" + tag + ".cu";
+    dump(prog_name, src.c_str());
+    for (int i = 0; i < rb_embedded_count; ++i) dump(base + rb_embedded_names[i], rb_embedded_sources[i]);
+  }
   nvrtcProgram prog = nullptr;
-  nvrtcResult res = n.CreateProgram(&prog, src.c_str(), "rb_ssa_jit.cu", rb_embedded_count, rb_embedded_sources,
+  nvrtcResult res = n.CreateProgram(&prog, src.c_str(), prog_name.c_str(), rb_embedded_count, rb_embedded_sources,
                                     rb_embedded_names);
   if (res != 0) return rb_fail(REBOP_ERR_NVRTC, std::string("nvrtcCreateProgram: ") + n.GetErrorString(res));
   const char* opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-lineinfo", "--std=c++17"};
