@@ -11,7 +11,8 @@
 
 struct RbCodegenInfo {
   unsigned block = 128;      // threads per CTA the kernel was generated for
-  unsigned net_words = 0;    // 32-bit words of shared memory for the packed stoichiometry table
+  unsigned net_words = 0;    // 32-bit words of dynamic shared memory the network needs (none)
+  unsigned static_smem = 0;  // bytes of static shared memory for the packed stoichiometry table
   bool uses_param_k = true;  // LMA rate constants are read from SsaRunParams::k
 };
 

@@ -52,7 +52,6 @@ struct rebop_batch {
   uint64_t events_total = 0, events_last = 0;
   int kernel_pref = REBOP_KERNEL_AUTO, kernel_used = REBOP_KERNEL_AUTO;
   uint32_t max_iters = 0;
-  uint32_t slow_batch = 4;  // parked ziggurat slow-path lanes per warp before they are served
   float last_ms = 0.f;
   RbTables tables;
   bool tables_ok = false;
@@ -374,7 +373,7 @@ static unsigned pow2_floor(unsigned v) {
 static unsigned choose_ring_depth(const rebop_batch* b, unsigned block, unsigned net_words, unsigned n_save,
                                   unsigned n_points, unsigned ctas_per_sm) {
   if (n_save == 0) return 1;
-  const size_t fixed = 4u * (RB_ZIG_WORDS + net_words);
+  const size_t fixed = RB_STATIC_SMEM_BYTES + 1024 + 4u * net_words;  // + per-CTA reservation
   const size_t per_depth = (size_t)(block / 32u) * n_save * 32u * 4u;
   const size_t budget = (size_t)b->max_smem_optin / (ctas_per_sm ? ctas_per_sm : 1);
   unsigned depth = 1;
@@ -407,7 +406,7 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   p.n_save = d_out ? n_save : 0;
   p.seed_mode = b->seed_mode;
   p.max_iters = b->max_iters;
-  p.slow_batch = b->slow_batch;
+  p.bias_hi = 0x43300000u;
   const unsigned n_points = step_last - step_first + 1;
 
   RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(rb_u64), b->stream));
@@ -431,7 +430,7 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     for (size_t r = 0; r < b->net.rx.size() && r < 64; ++r) p.k[r] = b->net.rx[r].k;
     const unsigned block = jit.block;
     const unsigned ctas = std::max(1u, 2048u / block / 2u);
-    p.ring_depth = choose_ring_depth(b, block, jit.net_words, p.n_save, n_points, ctas);
+    p.ring_depth = choose_ring_depth(b, block, jit.net_words + jit.static_smem / 4u, p.n_save, n_points, ctas);
     const size_t smem = RB_SSA_SMEM_BYTES(jit.net_words, block, p.ring_depth, p.n_save);
     const unsigned grid = (unsigned)((b->n + block - 1) / block);
     int st = rb_jit_launch(jit, p, grid, smem, b->stream);
@@ -445,7 +444,7 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     const unsigned net_words = S * block;
     p.ring_depth = choose_ring_depth(b, block, net_words, p.n_save, n_points, 8);
     const size_t smem = RB_SSA_SMEM_BYTES(net_words, block, p.ring_depth, p.n_save);
-    if (smem > (size_t)b->max_smem_optin)
+    if (smem + RB_STATIC_SMEM_BYTES > (size_t)b->max_smem_optin)
       return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: species state and sample ring do not fit in shared memory");
     const unsigned grid = (unsigned)((b->n + block - 1) / block);
     RB_CUDA(rb_table_launch(&b->tables, p, grid, smem, b->stream));

@@ -159,6 +159,7 @@ int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out) {
   e.k.kernel = kernel;
   e.k.block = info.block;
   e.k.net_words = info.net_words;
+  e.k.static_smem = info.static_smem;
   g_cache[key] = e;
   *out = e.k;
   return REBOP_OK;

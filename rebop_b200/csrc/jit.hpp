@@ -13,6 +13,7 @@ struct RbJitKernel {
   void* kernel = nullptr;  // cudaKernel_t
   unsigned block = 128;
   unsigned net_words = 0;
+  unsigned static_smem = 0;  // bytes of static shared memory beyond the ensemble loop's own
 };
 
 // Returns a compiled kernel for `net` on `device` (cached per process by source text).

@@ -7,8 +7,8 @@ typedef long long rb_i64;
 typedef unsigned int rb_u32;
 
 #define RB_FULL_MASK 0xffffffffu
-// 32-bit words of shared memory the ziggurat tables take: 256 (X[i], X[i+1]) pairs + 260 doubles of F
-#define RB_ZIG_WORDS (256 * 4 + 260 * 2)
+// Static shared memory of the ensemble loop (ziggurat tables: 256 (X[i], X[i+1]) pairs, 258 F, 256 chord slopes)
+#define RB_STATIC_SMEM_BYTES ((512 + 258 + 256) * 8)
 
 // Status bits written to SsaRunParams::status.
 #define RB_STATUS_ITER_CAP 1u  // a trajectory hit max_iters before reaching its last grid point
@@ -31,11 +31,11 @@ struct SsaRunParams {
   rb_u32 ring_depth;     // power of two, 1..32: grid points a warp can stage in shared memory
   rb_u32 seed_mode;      // 0 load rng, 1 seeds[], 2 seed_base + n
   rb_u32 max_iters;      // per-trajectory loop-iteration cap for this launch (0 = 2^32-1)
-  rb_u32 slow_batch;     // parked ziggurat slow-path lanes a warp waits for before serving them (0/1 = at once)
+  rb_u32 bias_hi;        // 0x43300000: high word of the biased-double species form (opaque to the compiler on purpose)
   rb_u64 save_mask[2];   // specialised kernels: bit s set => species s is sampled
   double k[64];          // specialised kernels: rate constants / parameters
 };
 
-// Shared memory (bytes) a launch needs: ziggurat tables + network tables + rings.
+// Dynamic shared memory (bytes) a launch needs: network tables + sample rings.
 #define RB_SSA_SMEM_BYTES(net_words, block, ring_depth, n_save) \
-  (4u * (RB_ZIG_WORDS + (net_words) + ((block) / 32u) * (ring_depth) * (n_save) * 32u))
+  (4u * ((net_words) + ((block) / 32u) * (ring_depth) * (n_save) * 32u))

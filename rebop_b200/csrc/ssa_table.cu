@@ -25,7 +25,7 @@ struct RbTableNet {
   static __device__ __forceinline__ int smem_words(const SsaRunParams&) {
     return c_tab.n_species * BLOCK;
   }
-  __device__ __forceinline__ void init(const SsaRunParams&, int* smem, rb_u32 tid) { xs = smem + tid; }
+  __device__ __forceinline__ void init(const SsaRunParams&, int* smem, rb_u32 tid, rb_u32) { xs = smem + tid; }
   __device__ __forceinline__ void load(const SsaRunParams& p, rb_u32 traj, bool valid) {
     const int S = c_tab.n_species;
     for (int s = 0; s < S; ++s) xs[s * BLOCK] = valid ? p.x[(size_t)s * p.ldn + traj] : 0;
