@@ -222,6 +222,8 @@ def run_gpu(args, model):
         batch.run_grid(args.tmax, nb)
         return batch.events()[1], batch.last_kernel_ms
 
+    lane_slots = 0
+
     # ---- value: device-resident -------------------------------------------------------
     for i in range(args.warmup):
         device_step(i)
@@ -238,6 +240,7 @@ def run_gpu(args, model):
         ev, ms = device_step(args.warmup + i)
         events += ev
         kernel_ms += ms
+        lane_slots += batch.lane_slots
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - w0
@@ -318,6 +321,7 @@ def run_gpu(args, model):
         "frac": achieved / (fp64_peak / 1e9) if achieved else None,
         "peak_source": "measured in this run: independent DADD/DMUL chains on all SMs at %.0f MHz" % fp64_mhz,
         "ops_per_event": F, "events_per_launch": ev_per_launch, "ms_per_launch": ms_per_launch,
+        "lane_efficiency": events / lane_slots if lane_slots else None,
         "traffic": traffic,
         "hbm": {"bound": "hbm", "achieved": sample_bytes / (ms_per_launch * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": sample_bytes / (ms_per_launch * 1e-3) / 1e9 / hbm_peak, "bytes_per_launch": sample_bytes,

@@ -159,6 +159,10 @@ int rebop_batch_sample_sums(rebop_batch* b, int64_t* sum, uint64_t* sumsq);
 int rebop_batch_sample_sums_device(rebop_batch* b, const int64_t** dev_ptr, uint32_t* n_rows);
 /* Applied reactions since creation, and during the last launch. */
 int rebop_batch_events(rebop_batch* b, uint64_t* total, uint64_t* last_launch);
+/* Lane slots of the last launch: 32 x the loop iterations each warp executed.  events / lane slots is
+ * the fraction of SIMT lanes that applied a reaction (the rest idled on finished trajectories,
+ * rejected ziggurat draws or grid crossings). */
+int rebop_batch_lane_slots(rebop_batch* b, uint64_t* last_launch);
 /* Device time of the last advance_until / run_grid launch in milliseconds (CUDA events). */
 int rebop_batch_last_kernel_ms(rebop_batch* b, float* ms);
 int rebop_batch_size(const rebop_batch* b, size_t* n_traj);

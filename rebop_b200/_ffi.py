@@ -88,6 +88,7 @@ SIGNATURES = {
     "rebop_batch_sample_sums": (C.c_int, [_vp, _i64p, _u64p]),
     "rebop_batch_sample_sums_device": (C.c_int, [_vp, C.POINTER(C.c_void_p), _u32p]),
     "rebop_batch_events": (C.c_int, [_vp, _u64p, _u64p]),
+    "rebop_batch_lane_slots": (C.c_int, [_vp, _u64p]),
     "rebop_batch_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rebop_batch_size": (C.c_int, [_vp, _szp]),
     "rebop_batch_synchronize": (C.c_int, [_vp]),
@@ -351,6 +352,13 @@ class Batch:
         tot, last = C.c_uint64(), C.c_uint64()
         check(lib.rebop_batch_events(self._h, C.byref(tot), C.byref(last)))
         return tot.value, last.value
+
+    @property
+    def lane_slots(self) -> int:
+        """32 x loop iterations of every warp in the last launch (events / lane_slots = SIMT lane efficiency)."""
+        v = C.c_uint64()
+        check(lib.rebop_batch_lane_slots(self._h, C.byref(v)))
+        return v.value
 
     @property
     def last_kernel_ms(self) -> float:

@@ -43,13 +43,13 @@ struct rebop_batch {
   size_t out_capacity = 0;  // int32 elements
   uint32_t out_rows = 0;    // (nb_steps+1) * n_save of the last run_grid
   uint32_t out_n_save = 0, out_nb_steps = 0;
-  rb_u64* d_counters = nullptr;  // [0] events, [1] status (low 32 bits)
+  rb_u64* d_counters = nullptr;  // [0] events, [1] status (low 32 bits), [2] lane slots
   rb_i64* d_sums = nullptr;
   size_t sums_capacity = 0;
   cudaStream_t stream = nullptr;      // the stream work is issued on
   cudaStream_t own_stream = nullptr;  // created with the batch; `stream` may point elsewhere
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  uint64_t events_total = 0, events_last = 0;
+  uint64_t events_total = 0, events_last = 0, lane_slots_last = 0;
   int kernel_pref = REBOP_KERNEL_AUTO, kernel_used = REBOP_KERNEL_AUTO;
   uint32_t max_iters = 0;
   float last_ms = 0.f;
@@ -248,8 +248,8 @@ extern "C" int rebop_batch_create(const rebop_network* net, int device, size_t n
   RB_CREATE_CUDA(cudaMalloc(&b->d_x, S * b->ldn * sizeof(int)));
   RB_CREATE_CUDA(cudaMalloc(&b->d_t, b->ldn * sizeof(double)));
   RB_CREATE_CUDA(cudaMalloc(&b->d_rng, 4 * b->ldn * sizeof(rb_u64)));
-  RB_CREATE_CUDA(cudaMalloc(&b->d_counters, 2 * sizeof(rb_u64)));
-  RB_CREATE_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(rb_u64), b->stream));
+  RB_CREATE_CUDA(cudaMalloc(&b->d_counters, 4 * sizeof(rb_u64)));
+  RB_CREATE_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
   RB_CREATE_CUDA(cudaMemsetAsync(b->d_rng, 0, 4 * b->ldn * sizeof(rb_u64), b->stream));
   RB_CREATE_CUDA(cudaMemsetAsync(b->d_t, 0, b->ldn * sizeof(double), b->stream));
   RB_CREATE_CUDA(cudaMemsetAsync(b->d_x, 0, S * b->ldn * sizeof(int), b->stream));
@@ -407,9 +407,12 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   p.seed_mode = b->seed_mode;
   p.max_iters = b->max_iters;
   p.bias_hi = 0x43300000u;
+  p.bias = 0x1.0p52 + 0x1.0p31;
+  p.one_m_eps = 1.0 - 0x1.0p-53;
+  for (int l = 0; l < 4; ++l) p.byte_sel[l] = 1 << (8 * l);
   const unsigned n_points = step_last - step_first + 1;
 
-  RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(rb_u64), b->stream));
+  RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
 
   // --- pick the kernel ---
   RbJitKernel jit;
@@ -453,12 +456,13 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   RB_CUDA(cudaEventRecord(b->ev1, b->stream));
   ++g_kernel_launches;
 
-  rb_u64 counters[2] = {0, 0};
+  rb_u64 counters[4] = {0, 0, 0, 0};
   RB_CUDA(cudaMemcpyAsync(counters, b->d_counters, sizeof counters, cudaMemcpyDeviceToHost, b->stream));
   RB_CUDA(cudaStreamSynchronize(b->stream));
   RB_CUDA(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
   b->seed_mode = 0;  // streams are live on the device from now on
   b->events_last = counters[0];
+  b->lane_slots_last = counters[2];
   b->events_total += counters[0];
   if (counters[1] & RB_STATUS_ITER_CAP)
     return rb_fail(REBOP_ERR_ITER_CAP, "a trajectory hit the per-launch iteration cap before reaching its target time");
@@ -576,6 +580,12 @@ extern "C" int rebop_batch_events(rebop_batch* b, uint64_t* total, uint64_t* las
   if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   if (total) *total = b->events_total;
   if (last_launch) *last_launch = b->events_last;
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_lane_slots(rebop_batch* b, uint64_t* last_launch) {
+  if (!b || !last_launch) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  *last_launch = b->lane_slots_last;
   return REBOP_OK;
 }
 

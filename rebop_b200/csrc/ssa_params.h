@@ -21,7 +21,7 @@ struct SsaRunParams {
   const rb_u64* seeds;   // [n_traj] or null; non-null => seed instead of loading rng
   rb_u64 seed_base;      // used when seed_mode == 2: seed_n = seed_base + n
   int* out;              // [(step-step_first)][n_save][ldn] samples, or null
-  rb_u64* events;        // [1] += applied reactions
+  rb_u64* events;        // [0] += applied reactions; [2] += lane slots (32 x loop iterations of each warp)
   rb_u32* status;        // [1] |= RB_STATUS_*
   double tmax;
   rb_u32 n_traj, ldn;
@@ -32,6 +32,11 @@ struct SsaRunParams {
   rb_u32 seed_mode;      // 0 load rng, 1 seeds[], 2 seed_base + n
   rb_u32 max_iters;      // per-trajectory loop-iteration cap for this launch (0 = 2^32-1)
   rb_u32 bias_hi;        // 0x43300000: high word of the biased-double species form (opaque to the compiler on purpose)
+  // Constants the hot loop reads straight from the parameter bank (one LDCU.128 per pair) instead of
+  // rebuilding them with two UMOVs each per iteration.
+  double bias;           // 2^52 + 2^31
+  double one_m_eps;      // 1 - 2^-53
+  int byte_sel[4];       // dp4a selectors 1, 1<<8, 1<<16, 1<<24
   rb_u64 save_mask[2];   // specialised kernels: bit s set => species s is sampled
   double k[64];          // specialised kernels: rate constants / parameters
 };
