@@ -49,9 +49,10 @@ typedef enum {
 
 /* Which kernel advances the ensemble. */
 typedef enum {
-  REBOP_KERNEL_AUTO = 0,   /* NVRTC-specialised when possible, else table-driven */
+  REBOP_KERNEL_AUTO = 0,   /* build-time kernel if one matches, else NVRTC-specialised, else table-driven */
   REBOP_KERNEL_TABLE = 1,  /* K1: generic kernel, network tables in __constant__ memory */
-  REBOP_KERNEL_NVRTC = 2   /* K2: network-specialised source compiled at run time */
+  REBOP_KERNEL_NVRTC = 2,  /* K2: network-specialised source compiled at run time */
+  REBOP_KERNEL_PREBUILT = 3 /* K2: network-specialised source compiled at build time (rebop_sysgen + nvcc) */
 } rebop_kernel_kind;
 
 /* Expression byte-code = post-order walk of `Expr` (src/expr.rs:9-21). */
@@ -70,6 +71,7 @@ typedef struct {
 typedef struct rebop_network rebop_network;
 typedef struct rebop_batch rebop_batch;
 typedef struct rebop_pexpr rebop_pexpr;
+typedef struct rebop_system rebop_system;
 
 const char* rebop_b200_last_error(void);
 const char* rebop_b200_version(void);
@@ -102,6 +104,30 @@ int rebop_network_nb_reactions(const rebop_network* net, uint32_t* out); /* src/
 int rebop_network_codegen(const rebop_network* net, char* buf, size_t cap, size_t* needed);
 int rebop_network_jit_cubin(const rebop_network* net, char* buf, size_t cap, size_t* needed);
 
+/* ---- define_system! (src/gillespie_macro.rs:49-129) ---- */
+
+/* Parses the macro's DSL text: `params...; Name { species, ... } rname: lhs => rhs @ rate ...`.
+ * Rate expressions may use parameters, literals, + - * / and parentheses (a rate that names a
+ * species -- the macro reads a stale per-call snapshot, src/gillespie_macro.rs:101-104 -- is
+ * rejected).  REBOP_ERR_PARSE on failure. */
+int rebop_system_parse(const char* dsl_text, rebop_system** out);
+void rebop_system_destroy(rebop_system* sys);
+int rebop_system_name(const rebop_system* sys, char* buf, size_t cap, size_t* needed);
+int rebop_system_counts(const rebop_system* sys, uint32_t* n_params, uint32_t* n_species, uint32_t* n_reactions);
+int rebop_system_param_name(const rebop_system* sys, uint32_t i, char* buf, size_t cap, size_t* needed);
+int rebop_system_species_name(const rebop_system* sys, uint32_t i, char* buf, size_t cap, size_t* needed);
+int rebop_system_reaction_name(const rebop_system* sys, uint32_t i, char* buf, size_t cap, size_t* needed);
+/* Name::with_parameters(p...) (src/gillespie_macro.rs:86-95): the network in define_system!
+ * arithmetic (REBOP_ARITH_MACRO), reactant factors in the order written (:106). */
+int rebop_system_network(const rebop_system* sys, const double* params, size_t n_params, rebop_network** out);
+/* The value of every reaction's rate expression for these parameter values (rates: [n_reactions]). */
+int rebop_system_rates(const rebop_system* sys, const double* params, size_t n_params, double* rates);
+/* Kernels rebop_sysgen + nvcc compiled into this library at build time (the .rsys files under rebop_b200/systems),
+ * and whether `net` would run on one of them (same structure; rate constants are launch parameters). */
+int rebop_b200_prebuilt_count(void);
+int rebop_b200_prebuilt_name(int i, char* buf, size_t cap, size_t* needed);
+int rebop_network_has_prebuilt(const rebop_network* net, int* yes);
+
 /* ---- rate expressions: the `PExpr` front end (src/expr.rs:43-273) ---- */
 
 /* "...".parse::<PExpr>() (src/expr.rs:134-141). REBOP_ERR_PARSE on failure. */
@@ -128,6 +154,11 @@ int rebop_batch_create(const rebop_network* net, int device, size_t n_traj, cons
 void rebop_batch_destroy(rebop_batch* b);
 int rebop_batch_set_kernel(rebop_batch* b, int kind);                 /* rebop_kernel_kind */
 int rebop_batch_get_kernel(const rebop_batch* b, int* kind);          /* the kernel the last launch used */
+/* New rate constants for the mass-action reactions of the batch's network (k: [n_reactions]; entries of
+ * expression reactions are ignored).  The struct define_system! generates exposes its parameters as
+ * plain fields that may change between advance_until calls (src/gillespie_macro.rs:62-67); trajectories,
+ * times and random streams are kept. */
+int rebop_batch_set_rates(rebop_batch* b, const double* k, size_t n_reactions);
 int rebop_batch_set_max_iters(rebop_batch* b, uint32_t max_iters);    /* watchdog per launch; 0 = 2^32-1 */
 /* Gillespie::seed (src/gillespie.rs:189-191) for every trajectory. */
 int rebop_batch_seed(rebop_batch* b, const uint64_t* seeds, uint64_t seed_base);

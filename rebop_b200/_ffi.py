@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "librebop_b200.so")
 
 OK, ERR_INVALID, ERR_OUT_OF_RANGE, ERR_PARSE, ERR_MISSING_PARAM, ERR_CUDA, ERR_NVRTC, ERR_LIMIT, ERR_ITER_CAP = range(9)
 ARITH_API, ARITH_MACRO = 0, 1
-KERNEL_AUTO, KERNEL_TABLE, KERNEL_NVRTC = 0, 1, 2
+KERNEL_AUTO, KERNEL_TABLE, KERNEL_NVRTC, KERNEL_PREBUILT = 0, 1, 2, 3
 OPCODES = dict(const=0, species=1, neg=2, add=3, sub=4, mul=5, div=6, pow=7, max=8, min=9, exp=10)
 
 
@@ -65,6 +65,18 @@ SIGNATURES = {
     "rebop_network_nb_reactions": (C.c_int, [_vp, _u32p]),
     "rebop_network_codegen": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
     "rebop_network_jit_cubin": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_system_parse": (C.c_int, [C.c_char_p, _pp]),
+    "rebop_system_destroy": (None, [_vp]),
+    "rebop_system_name": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_system_counts": (C.c_int, [_vp, _u32p, _u32p, _u32p]),
+    "rebop_system_param_name": (C.c_int, [_vp, C.c_uint32, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_system_species_name": (C.c_int, [_vp, C.c_uint32, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_system_reaction_name": (C.c_int, [_vp, C.c_uint32, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_system_network": (C.c_int, [_vp, _f64p, C.c_size_t, _pp]),
+    "rebop_system_rates": (C.c_int, [_vp, _f64p, C.c_size_t, _f64p]),
+    "rebop_b200_prebuilt_count": (C.c_int, []),
+    "rebop_b200_prebuilt_name": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_network_has_prebuilt": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "rebop_pexpr_parse": (C.c_int, [C.c_char_p, _pp]),
     "rebop_pexpr_destroy": (None, [_vp]),
     "rebop_pexpr_format": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
@@ -75,6 +87,7 @@ SIGNATURES = {
     "rebop_batch_set_kernel": (C.c_int, [_vp, C.c_int]),
     "rebop_batch_get_kernel": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "rebop_batch_set_max_iters": (C.c_int, [_vp, C.c_uint32]),
+    "rebop_batch_set_rates": (C.c_int, [_vp, _f64p, C.c_size_t]),
     "rebop_batch_seed": (C.c_int, [_vp, _u64p, C.c_uint64]),
     "rebop_batch_get_time": (C.c_int, [_vp, _f64p]),
     "rebop_batch_set_time": (C.c_int, [_vp, C.c_double]),
@@ -170,12 +183,22 @@ class PExpr:
 class Network:
     """Owning wrapper of a rebop_network handle."""
 
-    def __init__(self, n_species: int, arith: int = ARITH_API):
-        h = C.c_void_p()
-        check(lib.rebop_network_create(int(n_species), int(arith), C.byref(h)))
+    def __init__(self, n_species: int, arith: int = ARITH_API, _handle=None):
+        if _handle is None:
+            h = C.c_void_p()
+            check(lib.rebop_network_create(int(n_species), int(arith), C.byref(h)))
+        else:
+            h = _handle
         self._h = h
         self.n_species = int(n_species)
         self.arith = int(arith)
+
+    @property
+    def has_prebuilt(self) -> bool:
+        """True when a kernel compiled at build time (rebop_sysgen + nvcc) matches this network."""
+        yes = C.c_int()
+        check(lib.rebop_network_has_prebuilt(self._h, C.byref(yes)))
+        return bool(yes.value)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -228,6 +251,53 @@ class Network:
         return buf.raw
 
 
+def _string_out(fn, *args) -> str:
+    need = C.c_size_t()
+    check(fn(*args, None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    check(fn(*args, buf, need.value, None))
+    return buf.value.decode("utf-8")
+
+
+def prebuilt_systems() -> list:
+    """Names of the systems whose kernels were compiled into the library at build time."""
+    return [_string_out(lib.rebop_b200_prebuilt_name, i) for i in range(lib.rebop_b200_prebuilt_count())]
+
+
+class System:
+    """Owning wrapper of a rebop_system handle: parsed `define_system!` text."""
+
+    def __init__(self, dsl_text: str):
+        h = C.c_void_p()
+        check(lib.rebop_system_parse(dsl_text.encode("utf-8"), C.byref(h)))
+        self._h = h
+        self.name = _string_out(lib.rebop_system_name, h)
+        np_, ns, nr = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib.rebop_system_counts(h, C.byref(np_), C.byref(ns), C.byref(nr)))
+        self.params = [_string_out(lib.rebop_system_param_name, h, i) for i in range(np_.value)]
+        self.species = [_string_out(lib.rebop_system_species_name, h, i) for i in range(ns.value)]
+        self.reactions = [_string_out(lib.rebop_system_reaction_name, h, i) for i in range(nr.value)]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.rebop_system_destroy(self._h)
+            self._h = None
+
+    def rates(self, params) -> np.ndarray:
+        """Value of every reaction's rate expression for these parameter values."""
+        pv = np.ascontiguousarray(list(params) or [0.0], dtype=np.float64)
+        out = np.empty(max(1, len(self.reactions)), dtype=np.float64)
+        check(lib.rebop_system_rates(self._h, ptr(pv, C.c_double), len(list(params)), ptr(out, C.c_double)))
+        return out[:len(self.reactions)]
+
+    def network(self, params) -> Network:
+        """Name::with_parameters(...) -> network in define_system! arithmetic."""
+        pv = np.ascontiguousarray(list(params) or [0.0], dtype=np.float64)
+        h = C.c_void_p()
+        check(lib.rebop_system_network(self._h, ptr(pv, C.c_double), len(list(params)), C.byref(h)))
+        return Network(len(self.species), ARITH_MACRO, _handle=h)
+
+
 class Batch:
     """Owning wrapper of a rebop_batch handle: N trajectories resident on one GPU."""
 
@@ -272,6 +342,10 @@ class Batch:
         k = C.c_int()
         check(lib.rebop_batch_get_kernel(self._h, C.byref(k)))
         return k.value
+
+    def set_rates(self, k) -> None:
+        k = np.ascontiguousarray(k, dtype=np.float64)
+        check(lib.rebop_batch_set_rates(self._h, ptr(k, C.c_double), k.size))
 
     def set_max_iters(self, n: int) -> None:
         check(lib.rebop_batch_set_max_iters(self._h, int(n)))

@@ -265,13 +265,23 @@ extern "C" int rebop_batch_create(const rebop_network* net, int device, size_t n
 }
 
 extern "C" int rebop_batch_set_kernel(rebop_batch* b, int kind) {
-  if (!b || kind < REBOP_KERNEL_AUTO || kind > REBOP_KERNEL_NVRTC) return rb_fail(REBOP_ERR_INVALID, "bad kernel kind");
+  if (!b || kind < REBOP_KERNEL_AUTO || kind > REBOP_KERNEL_PREBUILT) return rb_fail(REBOP_ERR_INVALID, "bad kernel kind");
   b->kernel_pref = kind;
   return REBOP_OK;
 }
 extern "C" int rebop_batch_get_kernel(const rebop_batch* b, int* kind) {
   if (!b || !kind) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   *kind = b->kernel_used;
+  return REBOP_OK;
+}
+extern "C" int rebop_batch_set_rates(rebop_batch* b, const double* k, size_t n_reactions) {
+  if (!b || (!k && n_reactions)) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  if (n_reactions != b->net.rx.size()) return rb_fail(REBOP_ERR_INVALID, "n_reactions does not match the network");
+  for (size_t r = 0; r < n_reactions; ++r)
+    if (!b->net.rx[r].is_expr) b->net.rx[r].k = k[r];
+  int st = rb_lower_tables(b->net, &b->tables);
+  b->tables_ok = (st == REBOP_OK);
+  if (!b->tables_ok) b->tables_error = rebop_b200_last_error();
   return REBOP_OK;
 }
 extern "C" int rebop_batch_set_max_iters(rebop_batch* b, uint32_t max_iters) {
@@ -414,10 +424,20 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
 
   RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
 
-  // --- pick the kernel ---
+  // --- pick the kernel: build-time specialised, else NVRTC-specialised, else table-driven ---
   RbJitKernel jit;
   bool use_jit = false;
-  if (b->kernel_pref != REBOP_KERNEL_TABLE) {
+  int jit_kind = REBOP_KERNEL_NVRTC;
+  if (b->kernel_pref == REBOP_KERNEL_AUTO || b->kernel_pref == REBOP_KERNEL_PREBUILT) {
+    int st = rb_prebuilt_get(b->net, &jit);
+    if (st == REBOP_OK) {
+      use_jit = true;
+      jit_kind = REBOP_KERNEL_PREBUILT;
+    } else if (b->kernel_pref == REBOP_KERNEL_PREBUILT) {
+      return st;
+    }
+  }
+  if (!use_jit && (b->kernel_pref == REBOP_KERNEL_AUTO || b->kernel_pref == REBOP_KERNEL_NVRTC)) {
     int st = rb_jit_get(b->net, b->device, &jit);
     if (st == REBOP_OK) {
       use_jit = true;
@@ -438,7 +458,7 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     const unsigned grid = (unsigned)((b->n + block - 1) / block);
     int st = rb_jit_launch(jit, p, grid, smem, b->stream);
     if (st) return st;
-    b->kernel_used = REBOP_KERNEL_NVRTC;
+    b->kernel_used = jit_kind;
   } else {
     if (!b->tables_ok) return rb_fail(REBOP_ERR_LIMIT, b->tables_error);
     if (p.n_save > RB_TAB_MAX_SAVE) return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: more than 1024 saved species");

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "codegen.hpp"
+#include "sysgen.hpp"
 
 extern const char* const rb_embedded_names[];
 extern const char* const rb_embedded_sources[];
@@ -78,6 +79,49 @@ std::mutex g_mutex;
 std::map<std::pair<int, std::string>, CacheEntry> g_cache;
 
 }  // namespace
+
+// ---- kernels compiled at build time (rebop_sysgen + nvcc) ----
+static std::vector<RbPrebuilt>& prebuilt_registry() {
+  static std::vector<RbPrebuilt> r;  // filled by static initialisers of the generated translation units
+  return r;
+}
+void rb_register_prebuilt(const RbPrebuilt& entry) { prebuilt_registry().push_back(entry); }
+const RbPrebuilt* rb_find_prebuilt(const std::string& key) {
+  for (const RbPrebuilt& e : prebuilt_registry())
+    if (key == e.key) return &e;
+  return nullptr;
+}
+int rb_prebuilt_count() { return (int)prebuilt_registry().size(); }
+
+extern "C" int rebop_b200_prebuilt_count(void) { return rb_prebuilt_count(); }
+extern "C" int rebop_b200_prebuilt_name(int i, char* buf, size_t cap, size_t* needed) {
+  if (i < 0 || i >= rb_prebuilt_count()) return rb_fail(REBOP_ERR_OUT_OF_RANGE, "prebuilt kernel index out of range");
+  const std::string name = prebuilt_registry()[i].name;
+  if (needed) *needed = name.size() + 1;
+  if (buf && cap) {
+    std::strncpy(buf, name.c_str(), cap);
+    buf[cap - 1] = 0;
+  }
+  return REBOP_OK;
+}
+extern "C" int rebop_network_has_prebuilt(const rebop_network* net, int* yes) {
+  if (!net || !yes) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  std::string why;
+  *yes = rb_codegen_supported(*net, &why) && rb_find_prebuilt(rb_codegen_source(*net, "rb_ssa_jit", nullptr)) != nullptr;
+  return REBOP_OK;
+}
+
+int rb_prebuilt_get(const rebop_network& net, RbJitKernel* out) {
+  std::string why;
+  if (!rb_codegen_supported(net, &why)) return rb_fail(REBOP_ERR_LIMIT, "network cannot be specialised: " + why);
+  const RbPrebuilt* e = rb_find_prebuilt(rb_codegen_source(net, "rb_ssa_jit", nullptr));
+  if (!e) return rb_fail(REBOP_ERR_INVALID, "no build-time kernel was generated for this network (see rebop_b200/systems)");
+  out->kernel = const_cast<void*>(e->kernel);
+  out->block = e->block;
+  out->net_words = 0;
+  out->static_smem = e->static_smem;
+  return REBOP_OK;
+}
 
 // NVRTC: source text -> sm_100a cubin.  Needs no GPU.
 static int compile_to_cubin(const std::string& src, std::vector<char>* cubin) {

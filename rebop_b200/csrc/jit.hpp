@@ -20,6 +20,8 @@ struct RbJitKernel {
 // REBOP_ERR_LIMIT when the network is too large to specialise, REBOP_ERR_NVRTC when NVRTC is
 // missing or the compilation fails (the message carries the log).
 int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out);
+// The kernel rebop_sysgen + nvcc compiled for this network at build time, if any (REBOP_ERR_INVALID if none).
+int rb_prebuilt_get(const rebop_network& net, RbJitKernel* out);
 // Source (and optionally the sm_100a cubin) of the specialised kernel; needs no GPU.
 int rb_jit_compile(const rebop_network& net, std::string* source, std::vector<char>* cubin);
 int rb_jit_launch(const RbJitKernel& k, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
