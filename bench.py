@@ -319,7 +319,8 @@ def run_gpu(args, model):
         "kernel": "rb_ssa_jit" if kernel_used == _ffi.KERNEL_NVRTC else "rb_ssa_table_kernel",
         "bound": "fp64_issue", "achieved": achieved, "peak": fp64_peak / 1e9, "unit": "GFLOP/s (non-fused f64 ops)",
         "frac": achieved / (fp64_peak / 1e9) if achieved else None,
-        "peak_source": "measured in this run: independent DADD/DMUL chains on all SMs at %.0f MHz" % fp64_mhz,
+        "peak_source": "measured in this run (rebop_b200_measure_fp64_rate): 8 independent non-fused DADD/DMUL chains per "
+                       "thread on all SMs; MEASURED_PEAKS.json has no FP64 entry",
         "ops_per_event": F, "events_per_launch": ev_per_launch, "ms_per_launch": ms_per_launch,
         "lane_efficiency": events / lane_slots if lane_slots else None,
         "traffic": traffic,
@@ -371,8 +372,8 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "table", "nvrtc"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-traj-per-core", type=int, default=96, help="cpu_baseline sample size per host core")
-    ap.add_argument("--ref-traj-per-core", type=int, default=16, help="--impl reference: trajectories per core per step")
+    ap.add_argument("--cpu-traj-per-core", type=int, default=1024, help="cpu_baseline sample size per host core")
+    ap.add_argument("--ref-traj-per-core", type=int, default=128, help="--impl reference: trajectories per core per step")
     args = ap.parse_args()
 
     from rebop_b200 import models

@@ -1,0 +1,72 @@
+"""Tier-2 parity: ensemble distributions at every sample time, GPU vs the oracle's CPU runs.
+
+The two ensembles use *independent* seeds (disjoint seed ranges), so nothing here depends on the
+GPU reproducing the random stream: it checks the law of the process.  Tolerances: two-sample KS at
+family-wise alpha = 1e-3 (Bonferroni over steps x species), means within 5 standard errors,
+variances within 5 standard errors (stats_helpers.py).  The CPU tests show the harness accepts
+oracle-vs-oracle and rejects a 5 % change of one rate constant at the same sizes.
+"""
+import numpy as np
+import pytest
+
+from rebop_b200 import models
+from tests.helpers import oracle_network
+from tests.stats_helpers import compare_ensembles, ks_critical, ks_statistic
+
+ALPHA, Z = 1e-3, 5.0
+
+
+def test_ks_helpers():
+    assert ks_statistic([1, 2, 3], [1, 2, 3]) == 0.0
+    assert ks_statistic([0, 0, 0], [1, 1, 1]) == 1.0
+    assert abs(ks_critical(1000, 1000, 0.05) - 1.358 * np.sqrt(2 / 1000)) < 1e-3
+
+
+def test_harness_accepts_same_law_and_rejects_perturbed_model(oracle):
+    m = models.sir()
+    n = 6000
+    net = oracle_network(oracle, m)
+    a, _, _ = net.run_batch(m["x0"], models.seeds_sequence(n, 0), 250.0, 10, threads=8)
+    b, _, _ = net.run_batch(m["x0"], models.seeds_sequence(n, 10**6), 250.0, 10, threads=8)
+    assert compare_ensembles(a, b, ALPHA, Z) == []
+    m2 = models.sir(transmission=1.05e-4)
+    c, _, _ = oracle_network(oracle, m2).run_batch(m2["x0"], models.seeds_sequence(n, 2 * 10**6), 250.0, 10, threads=8)
+    assert compare_ensembles(a, c, ALPHA, Z) != []
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,tmax,nb_steps,arith", [
+    ("sir", 20000, 250.0, 10, 0),
+    ("dimers", 3000, 1.0, 4, 1),
+    ("mm_lma", 10000, 100.0, 10, 0),
+    ("vilar", 1500, 20.0, 10, 1),
+])
+def test_gpu_ensemble_matches_cpu_law(gpu, ffi, oracle, name, n, tmax, nb_steps, arith):
+    m = models.MODELS[name]()
+    ref, _, _ = oracle_network(oracle, m, arith).run_batch(m["x0"], models.seeds_sequence(n, 5 * 10**8), tmax, nb_steps, threads=8)
+    b = ffi.Batch(models.build_network(m, arith), n, m["x0"], seeds=None, seed_base=0)
+    b.run_grid(tmax, nb_steps)
+    out = b.samples()
+    b.close()
+    fails = compare_ensembles(out, ref, ALPHA, Z)
+    assert fails == [], "\n".join(fails[:10])
+
+
+@pytest.mark.gpu
+def test_device_moments_match_cpu_law(gpu, ffi, oracle):
+    """K4's exact sums give the same mean/variance as the samples, and agree with the CPU ensemble."""
+    from rebop_b200 import ensemble
+    m = models.sir()
+    n = 20000
+    b = ffi.Batch(models.build_network(m), n, m["x0"], seeds=None, seed_base=123)
+    b.run_grid(250.0, 10)
+    s1, s2 = b.sample_sums()
+    out = b.samples().astype(np.float64)
+    b.close()
+    mean, var = ensemble.finalize_stats(s1, s2, n)
+    np.testing.assert_allclose(mean, out.reshape(-1, n).mean(axis=1), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(var, out.reshape(-1, n).var(axis=1, ddof=1), rtol=1e-9, atol=1e-9)
+    ref, _, _ = oracle_network(oracle, m).run_batch(m["x0"], models.seeds_sequence(n, 7 * 10**8), 250.0, 10, threads=8)
+    ref = ref.reshape(-1, n).astype(np.float64)
+    se = np.sqrt(var / n + ref.var(axis=1, ddof=1) / n)
+    assert np.all(np.abs(mean - ref.mean(axis=1)) <= Z * se + 1e-12)
