@@ -207,7 +207,8 @@ def run_gpu(args, model):
     S = len(model["species"])
     nb = args.nb_steps
     net = models.build_network(model, _ffi.ARITH_MACRO)
-    kernel = {"auto": _ffi.KERNEL_AUTO, "table": _ffi.KERNEL_TABLE, "nvrtc": _ffi.KERNEL_NVRTC}[args.kernel]
+    kernel = {"auto": _ffi.KERNEL_AUTO, "table": _ffi.KERNEL_TABLE, "nvrtc": _ffi.KERNEL_NVRTC,
+              "prebuilt": _ffi.KERNEL_PREBUILT}[args.kernel]
 
     def shard_base(step_index):  # distinct trajectories every step and every rank
         return (step_index * world + rank) * n
@@ -316,7 +317,8 @@ def run_gpu(args, model):
         pass
     achieved = ev_per_launch * F / (ms_per_launch * 1e-3) / 1e9 if F else None
     roofline = {
-        "kernel": "rb_ssa_jit" if kernel_used == _ffi.KERNEL_NVRTC else "rb_ssa_table_kernel",
+        "kernel": {_ffi.KERNEL_TABLE: "rb_ssa_table_kernel (K1, table-driven)", _ffi.KERNEL_NVRTC: "rb_ssa_jit (K2, NVRTC)",
+                   _ffi.KERNEL_PREBUILT: "rb_ssa_sys_* (K2, built by rebop_sysgen + nvcc)"}.get(kernel_used, str(kernel_used)),
         "bound": "fp64_issue", "achieved": achieved, "peak": fp64_peak / 1e9, "unit": "GFLOP/s (non-fused f64 ops)",
         "frac": achieved / (fp64_peak / 1e9) if achieved else None,
         "peak_source": "measured in this run (rebop_b200_measure_fp64_rate): 8 independent non-fused DADD/DMUL chains per "
@@ -369,7 +371,7 @@ def main():
     ap.add_argument("--traj-per-gpu", type=int, default=TRAJ_PER_GPU)
     ap.add_argument("--tmax", type=float, default=None)
     ap.add_argument("--nb-steps", type=int, default=None)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "table", "nvrtc"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "table", "nvrtc", "prebuilt"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-traj-per-core", type=int, default=1024, help="cpu_baseline sample size per host core")

@@ -7,6 +7,8 @@
 // (tools/rebop_sysgen -> nvcc).  It has no CUDA dependency.
 #include "codegen.hpp"
 
+#include "ssa_params.h"
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -56,19 +58,124 @@ std::string emit_expr(const std::vector<rebop_expr_op>& prog) {
 
 }  // namespace
 
-bool rb_codegen_supported(const rebop_network& net, std::string* why) {
-  if (net.n_species > RB_GEN_MAX_SPECIES) {
-    if (why) *why = "more than " + std::to_string(RB_GEN_MAX_SPECIES) + " species (register-resident state)";
+static bool small_form_ok(const rebop_network& net) {
+  return net.n_species <= RB_GEN_MAX_SPECIES && net.rx.size() <= RB_GEN_MAX_REACTIONS;
+}
+
+// Large form: state as f64 columns in shared memory, unrolled propensity pass with checkpoints,
+// block re-walk from per-reaction records (ssa_kernel.cuh: rb_large_fire).
+static bool large_form_ok(const rebop_network& net, std::string* why) {
+  auto no = [&](const std::string& msg) {
+    if (why) *why = msg;
     return false;
-  }
-  if (net.rx.size() > RB_GEN_MAX_REACTIONS) {
-    if (why) *why = "more than " + std::to_string(RB_GEN_MAX_REACTIONS) + " reactions (register-resident cumulative sums)";
-    return false;
+  };
+  if (net.n_species > RB_GEN_LARGE_MAX_SPECIES) return no("more than " + std::to_string(RB_GEN_LARGE_MAX_SPECIES) + " species (shared-memory state)");
+  if (net.rx.size() > RB_MAX_K) return no("more than " + std::to_string(RB_MAX_K) + " reactions (rate constants in the launch parameters)");
+  for (const RbReaction& rx : net.rx) {
+    if (rx.is_expr) return no("expression rates in a network too large for register-resident state");
+    if (rx.term_idx.size() > 2) return no("a reaction with more than two reactant terms in a large network");
+    for (uint32_t e : rx.term_exp)
+      if (e > 2) return no("a reactant exponent above 2 in a large network");
+    int nz = 0;
+    for (int64_t d : rx.diff) nz += d != 0;
+    if (nz > 4) return no("a reaction changing more than four species in a large network");
+    // non-decreasing cumulative rates need counts that cannot go negative: every consumed species
+    // must be a reactant of at least that order (the propensity is 0 before the count would cross 0)
+    for (size_t sp = 0; sp < rx.diff.size(); ++sp) {
+      if (rx.diff[sp] >= 0) continue;
+      int64_t order = 0;
+      for (size_t j = 0; j < rx.term_idx.size(); ++j)
+        if (rx.term_idx[j] == sp) order += rx.term_exp[j] ? rx.term_exp[j] : 1;
+      if (order < -rx.diff[sp]) return no("a reaction consumes more of a species than its reactant order (counts could go negative)");
+    }
   }
   return true;
 }
 
+bool rb_codegen_supported(const rebop_network& net, std::string* why) {
+  return small_form_ok(net) || large_form_ok(net, why);
+}
+
+bool rb_codegen_is_large(const rebop_network& net) { return !small_form_ok(net); }
+
+static std::string large_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info) {
+  const int S = (int)net.n_species;
+  const int R = (int)net.rx.size();
+  const bool macro = net.arith == REBOP_ARITH_MACRO;
+  // CTA size: two CTAs of f64 state columns must fit in an SM's shared memory
+  unsigned block = 128;
+  while (block > 32 && (size_t)S * block * 8 > 100 * 1024) block /= 2;
+  int ckn = 8;
+  while ((R + ckn - 1) / ckn > 32) ckn *= 2;  // at most 32 checkpoints (64 registers)
+  const int nck = (R + ckn - 1) / ckn;
+  unsigned tick = 16;
+  if (const char* env = std::getenv("REBOP_B200_CODEGEN")) {
+    const std::string e(env);
+    const size_t pos = e.find("lblock=");
+    if (pos != std::string::npos) block = (unsigned)std::atoi(e.c_str() + pos + 7);
+  }
+  if (info) {
+    info->block = block;
+    info->net_words = (unsigned)(S * block * 2);
+    info->static_smem = 16;
+    info->large = true;
+  }
+  std::ostringstream o;
+  o << "// generated by rebop_b200 codegen (large form): " << S << " species, " << R << " reactions, "
+    << (macro ? "define_system! arithmetic" : "function-API arithmetic") << ", " << nck << " checkpoints of " << ckn
+    << " reactions\n";
+  o << "#define RB_TICK " << tick << "u\n";
+  o << "#include \"ssa_kernel.cuh\"\n\n";
+  o << "struct RbGenNet {\n";
+  o << "  static constexpr int BLOCK = " << block << ";\n";
+  o << "  double* xs;  // this thread's column of the f64 state: species s at xs[s * BLOCK]\n";
+  o << "  double ck[" << nck << "];  // cumulative rate after every " << ckn << " reactions\n";
+  o << "  static __device__ __forceinline__ int smem_words(const SsaRunParams&) { return " << S * (int)block * 2 << "; }\n";
+  o << "  __device__ __forceinline__ void init(const SsaRunParams&, int* smem, rb_u32 tid, rb_u32) {\n";
+  o << "    xs = reinterpret_cast<double*>(smem) + tid;\n  }\n";
+  o << "  __device__ __forceinline__ void load(const SsaRunParams& p, rb_u32 traj, bool valid) {\n";
+  o << "    for (int s = 0; s < " << S << "; ++s) xs[s * BLOCK] = valid ? (double)p.x[(size_t)s * p.ldn + traj] : 0.0;\n  }\n";
+  o << "  __device__ __forceinline__ void store(const SsaRunParams& p, rb_u32 traj) {\n";
+  o << "    for (int s = 0; s < " << S << "; ++s) p.x[(size_t)s * p.ldn + traj] = __double2int_rn(xs[s * BLOCK]);\n  }\n";
+  // unrolled propensities; the arithmetic of every term is the one rb_large_term re-walks
+  o << "  __device__ __forceinline__ double propensities(const SsaRunParams& p) {\n";
+  o << "    double c = 0.0, a;\n";
+  if (R == 0) o << "    (void)a;\n";
+  for (int r = 0; r < R; ++r) {
+    const RbReaction& rx = net.rx[r];
+    std::string a = "p.k[" + std::to_string(r) + "]";
+    for (size_t j = 0; j < rx.term_idx.size(); ++j) {
+      const std::string x = "xs[" + std::to_string(rx.term_idx[j]) + " * BLOCK]";
+      const unsigned e = rx.term_exp[j];
+      if (e <= 1) a = "__dmul_rn(" + a + ", " + x + ")";
+      else if (macro) a = "__dmul_rn(" + a + ", __dmul_rn(" + x + ", __dsub_rn(" + x + ", 1.0)))";
+      else a = "__dmul_rn(__dmul_rn(" + a + ", __dsub_rn(" + x + ", 1.0)), " + x + ")";
+    }
+    o << "    a = " << a << ";\n";
+    o << "    c = __dadd_rn(c, a);\n";
+    if (r % ckn == ckn - 1 || r == R - 1) o << "    ck[" << r / ckn << "] = c;\n";
+  }
+  o << "    return c;\n  }\n";
+  o << "  __device__ __forceinline__ bool fire(const SsaRunParams& p, double chosen) {\n";
+  if (R == 0) o << "    return false;\n";
+  else o << "    return rb_large_fire<" << nck << ", " << ckn << ", " << R << ", " << (macro ? "true" : "false")
+         << ", BLOCK>(ck, chosen, xs, p.gtab);\n";
+  o << "  }\n";
+  o << "  __device__ __forceinline__ void record(const SsaRunParams& p, int* dst, rb_u32 stride) const {\n";
+  o << "    const rb_u32* save = p.gtab + " << R * 8 << ";\n";
+  o << "    for (rb_u32 j = 0; j < p.n_save; ++j) dst[(size_t)j * stride] = __double2int_rn(xs[__ldg(save + j) * BLOCK]);\n";
+  o << "  }\n};\n\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(" << block << ", 2) " << kernel_name
+    << "(const __grid_constant__ SsaRunParams p) {\n";
+  o << "  extern __shared__ __align__(16) int rb_smem[];\n";
+  o << "  RbGenNet net;\n";
+  o << "  rb_ssa_loop(net, p, rb_smem);\n";
+  o << "}\n";
+  return o.str();
+}
+
 std::string rb_codegen_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info) {
+  if (!small_form_ok(net)) return large_source(net, kernel_name, info);
   const int S = (int)net.n_species;
   const int R = (int)net.rx.size();
   const bool macro = net.arith == REBOP_ARITH_MACRO;

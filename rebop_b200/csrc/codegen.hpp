@@ -8,14 +8,19 @@
 // larger ones use the table-driven kernel (shared-memory state).
 #define RB_GEN_MAX_SPECIES 32
 #define RB_GEN_MAX_REACTIONS 48
+// Large form (f64 state columns in shared memory): 32-thread CTAs hold up to 100 KB / (32 * 8 B) species.
+#define RB_GEN_LARGE_MAX_SPECIES 400
 
 struct RbCodegenInfo {
   unsigned block = 128;      // threads per CTA the kernel was generated for
   unsigned net_words = 0;    // 32-bit words of dynamic shared memory the network needs (none)
   unsigned static_smem = 0;  // bytes of static shared memory for the packed stoichiometry table
   bool uses_param_k = true;  // LMA rate constants are read from SsaRunParams::k
+  bool large = false;        // large form: needs SsaRunParams::gtab (reaction records + saved-species list)
 };
 
 bool rb_codegen_supported(const rebop_network& net, std::string* why);
+// True when the network gets the large form (state in shared memory) instead of register-resident state.
+bool rb_codegen_is_large(const rebop_network& net);
 // Source text of `extern "C" __global__ void <kernel_name>(SsaRunParams)`; includes "ssa_kernel.cuh".
 std::string rb_codegen_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info);

@@ -57,6 +57,10 @@ struct rebop_batch {
   bool tables_ok = false;
   std::string tables_error;
   int max_smem_optin = 0, sm_count = 0;
+  bool x_nonneg = true;           // every count uploaded so far was >= 0 (large specialised kernels need it)
+  rb_u32* d_gtab = nullptr;       // large specialised kernels: reaction records + saved-species list
+  size_t gtab_capacity = 0;       // words
+  std::vector<rb_u32> h_gtab;
 };
 
 // ---------------------------------------------------------------------------
@@ -160,9 +164,13 @@ static int upload_x0(rebop_batch* b, const int64_t* x0, int per_traj) {
   if (S == 0) return REBOP_OK;
   if (!x0) return rb_fail(REBOP_ERR_INVALID, "x0 is NULL");
   const size_t count = per_traj ? b->n * S : S;
-  for (size_t i = 0; i < count; ++i)
+  bool nonneg = true;
+  for (size_t i = 0; i < count; ++i) {
     if (x0[i] < INT32_MIN || x0[i] > INT32_MAX)
       return rb_fail(REBOP_ERR_LIMIT, "initial species count outside the int32 range carried on the device");
+    nonneg = nonneg && x0[i] >= 0;
+  }
+  b->x_nonneg = nonneg;
   if (!per_traj) {
     std::vector<int> h(S);
     for (uint32_t s = 0; s < S; ++s) h[s] = (int)x0[s];
@@ -207,7 +215,7 @@ extern "C" void rebop_batch_destroy(rebop_batch* b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   if (b->own_stream && b->own_stream != b->stream) cudaStreamSynchronize(b->own_stream);
   cudaFree(b->d_x); cudaFree(b->d_t); cudaFree(b->d_rng); cudaFree(b->d_seeds);
-  cudaFree(b->d_out); cudaFree(b->d_counters); cudaFree(b->d_sums);
+  cudaFree(b->d_out); cudaFree(b->d_counters); cudaFree(b->d_sums); cudaFree(b->d_gtab);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->own_stream) cudaStreamDestroy(b->own_stream);
@@ -386,8 +394,8 @@ static unsigned choose_ring_depth(const rebop_batch* b, unsigned block, unsigned
   const size_t fixed = RB_STATIC_SMEM_BYTES + 1024 + 4u * net_words;  // + per-CTA reservation
   const size_t per_depth = (size_t)(block / 32u) * n_save * 32u * 4u;
   const size_t budget = (size_t)b->max_smem_optin / (ctas_per_sm ? ctas_per_sm : 1);
-  unsigned depth = 1;
-  if (budget > fixed + per_depth) depth = (unsigned)std::min<size_t>(32, (budget - fixed) / per_depth);
+  if (budget < fixed + per_depth) return 0;  // no room for a ring: samples go straight to global memory
+  unsigned depth = (unsigned)std::min<size_t>(32, (budget - fixed) / per_depth);
   depth = pow2_floor(depth ? depth : 1);
   unsigned cap = 1;
   while (cap < n_points && cap < 32) cap *= 2;
@@ -446,15 +454,59 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     }
   }
 
+  // large specialised kernels assume non-decreasing cumulative rates: k >= 0 and counts >= 0
+  if (use_jit && jit.large) {
+    bool ok = b->x_nonneg;
+    for (const RbReaction& rx : b->net.rx) ok = ok && !(rx.k < 0.0);
+    if (!ok) {
+      if (b->kernel_pref != REBOP_KERNEL_AUTO)
+        return rb_fail(REBOP_ERR_LIMIT, "the specialised kernel for large networks needs rate constants >= 0 and counts >= 0");
+      use_jit = false;
+    }
+  }
+
   RB_CUDA(cudaEventRecord(b->ev0, b->stream));
   if (use_jit) {
     // saved species: the specialised kernels take a bit mask and emit rows in ascending species order
-    for (uint32_t j = 0; j < p.n_save; ++j) p.save_mask[save_idx[j] >> 6] |= 1ull << (save_idx[j] & 63u);
-    for (size_t r = 0; r < b->net.rx.size() && r < 64; ++r) p.k[r] = b->net.rx[r].k;
+    for (uint32_t j = 0; j < p.n_save && save_idx[j] < 128; ++j) p.save_mask[save_idx[j] >> 6] |= 1ull << (save_idx[j] & 63u);
+    for (size_t r = 0; r < b->net.rx.size() && r < RB_MAX_K; ++r) p.k[r] = b->net.rx[r].k;
     const unsigned block = jit.block;
-    const unsigned ctas = std::max(1u, 2048u / block / 2u);
+    unsigned ctas = std::max(1u, 2048u / block / 2u);
+    if (jit.large) {
+      ctas = 2;
+      // reaction records (see ssa_params.h) + saved-species list
+      const size_t R = b->net.rx.size();
+      b->h_gtab.assign(R * RB_GTAB_WORDS_PER_REACTION + std::max<uint32_t>(p.n_save, 1), 0u);
+      for (size_t r = 0; r < R; ++r) {
+        const RbReaction& rx = b->net.rx[r];
+        rb_u32* w = b->h_gtab.data() + r * RB_GTAB_WORDS_PER_REACTION;
+        std::memcpy(w, &rx.k, 8);
+        const size_t nt = rx.term_idx.size();
+        w[2] = (nt > 0 ? rx.term_idx[0] : 0u) | ((nt > 1 ? rx.term_idx[1] : 0u) << 16);
+        w[3] = (nt > 0 ? rx.term_exp[0] : 0u) | ((nt > 1 ? rx.term_exp[1] : 0u) << 8) | ((rb_u32)nt << 16);
+        unsigned q = 0;
+        for (uint32_t sp = 0; sp < S && q < 4; ++sp) {
+          if (rx.diff[sp] == 0) continue;
+          w[4 + q / 2] |= sp << (16 * (q & 1));
+          w[6 + q / 2] |= ((rb_u32)(uint16_t)(int16_t)rx.diff[sp]) << (16 * (q & 1));
+          ++q;
+        }
+      }
+      for (uint32_t j = 0; j < p.n_save; ++j) b->h_gtab[R * RB_GTAB_WORDS_PER_REACTION + j] = save_idx[j];
+      if (b->h_gtab.size() > b->gtab_capacity) {
+        if (b->d_gtab) RB_CUDA(cudaFree(b->d_gtab));
+        b->d_gtab = nullptr;
+        b->gtab_capacity = 0;
+        RB_CUDA(cudaMalloc(&b->d_gtab, b->h_gtab.size() * sizeof(rb_u32)));
+        b->gtab_capacity = b->h_gtab.size();
+      }
+      RB_CUDA(cudaMemcpyAsync(b->d_gtab, b->h_gtab.data(), b->h_gtab.size() * sizeof(rb_u32), cudaMemcpyHostToDevice, b->stream));
+      p.gtab = b->d_gtab;
+    }
     p.ring_depth = choose_ring_depth(b, block, jit.net_words + jit.static_smem / 4u, p.n_save, n_points, ctas);
     const size_t smem = RB_SSA_SMEM_BYTES(jit.net_words, block, p.ring_depth, p.n_save);
+    if (smem + RB_STATIC_SMEM_BYTES + jit.static_smem > (size_t)b->max_smem_optin)
+      return rb_fail(REBOP_ERR_LIMIT, "specialised kernel: species state does not fit in shared memory");
     const unsigned grid = (unsigned)((b->n + block - 1) / block);
     int st = rb_jit_launch(jit, p, grid, smem, b->stream);
     if (st) return st;

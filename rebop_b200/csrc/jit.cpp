@@ -118,8 +118,9 @@ int rb_prebuilt_get(const rebop_network& net, RbJitKernel* out) {
   if (!e) return rb_fail(REBOP_ERR_INVALID, "no build-time kernel was generated for this network (see rebop_b200/systems)");
   out->kernel = const_cast<void*>(e->kernel);
   out->block = e->block;
-  out->net_words = 0;
+  out->net_words = e->net_words;
   out->static_smem = e->static_smem;
+  out->large = rb_codegen_is_large(net);
   return REBOP_OK;
 }
 
@@ -204,6 +205,7 @@ int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out) {
   e.k.block = info.block;
   e.k.net_words = info.net_words;
   e.k.static_smem = info.static_smem;
+  e.k.large = info.large;
   g_cache[key] = e;
   *out = e.k;
   return REBOP_OK;

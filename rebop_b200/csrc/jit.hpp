@@ -14,6 +14,7 @@ struct RbJitKernel {
   unsigned block = 128;
   unsigned net_words = 0;
   unsigned static_smem = 0;  // bytes of static shared memory beyond the ensemble loop's own
+  bool large = false;        // large form: the launch needs SsaRunParams::gtab
 };
 
 // Returns a compiled kernel for `net` on `device` (cached per process by source text).

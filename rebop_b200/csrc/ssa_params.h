@@ -10,6 +10,16 @@ typedef unsigned int rb_u32;
 // Static shared memory of the ensemble loop (ziggurat tables: 256 (X[i], X[i+1]) pairs, 258 F, 256 chord slopes)
 #define RB_STATIC_SMEM_BYTES ((512 + 258 + 256) * 8)
 
+// Rate constants carried in the launch parameters (bounds the reactions a specialised kernel can have).
+#define RB_MAX_K 1024
+
+// Record of one reaction in SsaRunParams::gtab (8 words, built by the engine at launch):
+//   w0,w1  rate constant (f64)            w2  species of term 0 | species of term 1 << 16
+//   w3     exponent 0 | exponent 1 << 8 | number of terms << 16
+//   w4,w5  jump species 0..3 (u16 each)   w6,w7  jump differences 0..3 (i16 each, 0 = unused)
+// followed, after the last reaction, by the saved-species list (one word each).
+#define RB_GTAB_WORDS_PER_REACTION 8
+
 // Status bits written to SsaRunParams::status.
 #define RB_STATUS_ITER_CAP 1u  // a trajectory hit max_iters before reaching its last grid point
 
@@ -38,7 +48,8 @@ struct SsaRunParams {
   double one_m_eps;      // 1 - 2^-53
   int byte_sel[4];       // dp4a selectors 1, 1<<8, 1<<16, 1<<24
   rb_u64 save_mask[2];   // specialised kernels: bit s set => species s is sampled
-  double k[64];          // specialised kernels: rate constants / parameters
+  const rb_u32* gtab;    // large specialised kernels: per-reaction records + saved-species list in global memory
+  double k[RB_MAX_K];    // specialised kernels: rate constants (kernel parameters may be up to 32 KB on sm_70+)
 };
 
 // Dynamic shared memory (bytes) a launch needs: network tables + sample rings.

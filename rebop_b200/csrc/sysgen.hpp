@@ -36,7 +36,7 @@ int rb_system_network(const rebop_system& sys, const double* params, size_t n_pa
 struct RbPrebuilt {
   const char* key;      // rb_codegen_source(net, "rb_ssa_jit") of the network it was generated from
   const void* kernel;   // __global__ function
-  unsigned block, static_smem;
+  unsigned block, static_smem, net_words;
   const char* name;     // system name
 };
 void rb_register_prebuilt(const RbPrebuilt& entry);

@@ -68,6 +68,23 @@ def mm_lma():
                 reactions=[_lma(S, 0.0017, [0, 1], [2]), _lma(S, 0.5, [2], [0, 1]), _lma(S, 0.1, [2], [3])])
 
 
+def ring(n=50, k=1.0, a0=1000, tmax=100.0, nb_steps=10):
+    """benchmarks/benches/my_benchmark.rs:601-614 (api_ring): X_i -> X_(i+1 mod n), all mass on X_0."""
+    rx = [_lma(n, k, [i], [(i + 1) % n]) for i in range(n)]
+    return dict(name="ring", species=["A%d" % i for i in range(n)], x0=[a0] + [0] * (n - 1), tmax=float(tmax),
+                nb_steps=nb_steps, params=[k], reactions=rx)
+
+
+def flocculation(n=50, k=1.0, n0=1000, tmax=1000.0, nb_steps=10):
+    """benchmarks/benches/my_benchmark.rs:683-700 (api_flocculation): A_i + A_j -> A_(i+j), i <= j, i + j <= n."""
+    rx = []
+    for i in range(1, n // 2 + 1):
+        for j in range(i, n - i + 1):
+            rx.append(_lma(n, k, [i - 1, j - 1], [i + j - 1]))
+    return dict(name="flocculation", species=["A%d" % (i + 1) for i in range(n)], x0=[n0] + [0] * (n - 1),
+                tmax=float(tmax), nb_steps=nb_steps, params=[k], reactions=rx)
+
+
 def _splitmix64(state):
     state = (state + 0x9E3779B97F4A7C15) & (2**64 - 1)
     z = state
@@ -76,7 +93,7 @@ def _splitmix64(state):
     return state, z ^ (z >> 31)
 
 
-def synthetic(n_species=100, n_reactions=500, gen_seed=20240501, tmax=0.05, nb_steps=100):
+def synthetic(n_species=100, n_reactions=500, gen_seed=20240501, tmax=0.2, nb_steps=100):
     """Deterministic random mass-action network (not in the reference).
 
     Species s has mass 1 + (s mod 3); reactions come in reversible pairs: with probability 0.4 an
@@ -128,7 +145,7 @@ def synthetic(n_species=100, n_reactions=500, gen_seed=20240501, tmax=0.05, nb_s
                 params=[r[0] for r in rx], reactions=rx)
 
 
-MODELS = dict(sir=sir, dimers=dimers, vilar=vilar, mm_lma=mm_lma, synthetic=synthetic)
+MODELS = dict(sir=sir, dimers=dimers, vilar=vilar, mm_lma=mm_lma, synthetic=synthetic, ring=ring, flocculation=flocculation)
 
 
 def build_network(model, arith=0):

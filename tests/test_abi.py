@@ -188,10 +188,25 @@ def test_nvrtc_compiles_sm100a_cubin_without_gpu(ffi):
     assert cubin[:4] == b"\x7fELF" and len(cubin) > 10000
 
 
-def test_large_network_is_not_specialised(ffi):
+def test_large_network_gets_the_shared_memory_form(ffi):
+    """100 species / 500 reactions: f64 state columns in shared memory, checkpointed cumulative sums."""
     model = models.synthetic()
     net = models.build_network(model)
     assert net.nb_reactions == 500
+    src = net.codegen()
+    assert "large form" in src and "32 checkpoints of 16 reactions" in src and "rb_large_fire<32, 16, 500, false, BLOCK>" in src
+    assert "static constexpr int BLOCK = 128;" in src
+    cubin = net.jit_cubin()  # NVRTC, sm_100a, no GPU needed
+    assert cubin[:4] == b"\x7fELF"
+
+
+def test_network_no_specialised_form_can_hold(ffi):
+    """Three reactant terms in a network beyond the register-resident limits: only the table-driven kernel runs it."""
+    S = 40
+    net = ffi.Network(S)
+    diff = [0] * S
+    diff[0], diff[1], diff[2], diff[3] = -1, -1, -1, 1
+    net.add_reaction_lma_sparse(1.0, [(0, 1), (1, 1), (2, 1)], diff)
     with pytest.raises(ffi.RebopError) as e:
         net.codegen()
     assert e.value.status == ffi.ERR_LIMIT

@@ -33,6 +33,47 @@ def test_bit_exact_vs_oracle(gpu, ffi, oracle, kernel, arith, name, n, tmax, nb_
     assert ev == ref_tot
 
 
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("name,kwargs,n,tmax,nb_steps", [
+    ("synthetic", {}, 160, 0.02, 5),                 # BASELINE config C5: 100 species, 500 reactions
+    ("flocculation", {"n": 50}, 96, 0.02, 4),        # my_benchmark.rs:683-700: 50 species, 625 reactions
+    ("ring", {"n": 50}, 96, 2.0, 4),                 # my_benchmark.rs:601-614: 50 species, 50 reactions
+    ("ring", {"n": 300, "a0": 200}, 40, 1.0, 2),     # 300 species: 32-thread CTAs
+])
+def test_large_networks_bit_exact(gpu, ffi, oracle, arith, name, kwargs, n, tmax, nb_steps):
+    """Networks beyond the register-resident limits: the shared-memory specialised form (NVRTC) and the
+    table-driven kernel against the oracle."""
+    model = models.MODELS[name](**kwargs)
+    seeds = numpy_seeds(n, rng=11)
+    ref, _, ref_tot = oracle_network(oracle, model, arith).run_batch(model["x0"], seeds, tmax, nb_steps, threads=8)
+    assert ref_tot > 50 * n
+    for kernel in ("nvrtc", "table"):
+        out, ev, used = run_product(ffi, model, seeds, tmax, nb_steps, KERNELS[kernel], arith)
+        assert used == KERNELS[kernel]
+        np.testing.assert_array_equal(out, ref)
+        assert ev == ref_tot
+    # a subset of the species, in the middle of the index range
+    save = [3, 17, len(model["species"]) - 1]
+    out, _, _ = run_product(ffi, model, seeds, tmax, nb_steps, KERNELS["nvrtc"], arith, save_idx=save)
+    np.testing.assert_array_equal(out, ref[:, save, :])
+
+
+def test_large_form_falls_back_when_counts_can_be_negative(gpu, ffi, oracle):
+    """A negative initial count breaks the monotone cumulative sums the large form relies on: AUTO falls back
+    to the table-driven kernel, an explicit NVRTC request is refused."""
+    model = models.ring(n=50)
+    x0 = list(model["x0"])
+    x0[7] = -3
+    seeds = numpy_seeds(32, rng=3)
+    ref, _, tot = oracle_network(oracle, model).run_batch(x0, seeds, 0.5, 2)
+    out, ev, used = run_product(ffi, model, seeds, 0.5, 2, 0, x0=x0)
+    assert used == KERNELS["table"]
+    np.testing.assert_array_equal(out, ref)
+    with pytest.raises(ffi.RebopError) as e:
+        run_product(ffi, model, seeds, 0.5, 2, KERNELS["nvrtc"], x0=x0)
+    assert e.value.status == ffi.ERR_LIMIT
+
+
 @pytest.mark.parametrize("kernel", ["table", "nvrtc"])
 @pytest.mark.parametrize("n", [1, 31, 33, 127, 129, 1000])
 def test_ragged_sizes(gpu, ffi, oracle, kernel, n):
