@@ -159,7 +159,13 @@ int rebop_batch_get_kernel(const rebop_batch* b, int* kind);          /* the ker
  * plain fields that may change between advance_until calls (src/gillespie_macro.rs:62-67); trajectories,
  * times and random streams are kept. */
 int rebop_batch_set_rates(rebop_batch* b, const double* k, size_t n_reactions);
-int rebop_batch_set_max_iters(rebop_batch* b, uint32_t max_iters);    /* watchdog per launch; 0 = 2^32-1 */
+int rebop_batch_set_max_iters(rebop_batch* b, uint32_t max_iters);
+/* How trajectories are mapped to SIMT lanes.  1 = static: thread n runs trajectory n, samples are staged in
+ * shared memory and written as full 128-byte lines.  2 = dynamic: a resident grid, a lane whose trajectory is
+ * finished claims the next one from a counter (no lane idles behind the slowest trajectory of its warp; samples
+ * are stored one by one).  0 = auto.  Results are identical: every trajectory owns its state and random stream. */
+int rebop_batch_set_schedule(rebop_batch* b, int schedule);
+int rebop_batch_get_schedule(const rebop_batch* b, int* schedule_used); /* of the last launch: 1 or 2 */    /* watchdog per launch; 0 = 2^32-1 */
 /* Gillespie::seed (src/gillespie.rs:189-191) for every trajectory. */
 int rebop_batch_seed(rebop_batch* b, const uint64_t* seeds, uint64_t seed_base);
 /* get/set_time, get/set_species (src/gillespie.rs:246-267). species: [n_traj][n_species]. */

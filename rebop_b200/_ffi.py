@@ -87,6 +87,8 @@ SIGNATURES = {
     "rebop_batch_set_kernel": (C.c_int, [_vp, C.c_int]),
     "rebop_batch_get_kernel": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "rebop_batch_set_max_iters": (C.c_int, [_vp, C.c_uint32]),
+    "rebop_batch_set_schedule": (C.c_int, [_vp, C.c_int]),
+    "rebop_batch_get_schedule": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "rebop_batch_set_rates": (C.c_int, [_vp, _f64p, C.c_size_t]),
     "rebop_batch_seed": (C.c_int, [_vp, _u64p, C.c_uint64]),
     "rebop_batch_get_time": (C.c_int, [_vp, _f64p]),
@@ -346,6 +348,16 @@ class Batch:
     def set_rates(self, k) -> None:
         k = np.ascontiguousarray(k, dtype=np.float64)
         check(lib.rebop_batch_set_rates(self._h, ptr(k, C.c_double), k.size))
+
+    def set_schedule(self, schedule: int) -> None:
+        """0 auto, 1 static, 2 dynamic (see rebop_batch_set_schedule)."""
+        check(lib.rebop_batch_set_schedule(self._h, int(schedule)))
+
+    @property
+    def schedule_used(self) -> int:
+        v = C.c_int()
+        check(lib.rebop_batch_get_schedule(self._h, C.byref(v)))
+        return v.value
 
     def set_max_iters(self, n: int) -> None:
         check(lib.rebop_batch_set_max_iters(self._h, int(n)))

@@ -195,7 +195,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
       if (rx.diff[s] != 0) touched[s] = true;
 
   // development knobs (REBOP_B200_CODEGEN="block=128,minctas=0,tick=16"); the defaults are the tuned values
-  unsigned block = 128, minctas = 0, tick = 16;
+  unsigned block = 128, minctas = 5, tick = 16;  // 5 CTAs of 128 threads: at most 96 registers per thread
   if (const char* env = std::getenv("REBOP_B200_CODEGEN")) {
     const std::string e(env);
     auto get = [&](const char* key, unsigned def) {

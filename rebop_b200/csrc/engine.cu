@@ -57,6 +57,8 @@ struct rebop_batch {
   bool tables_ok = false;
   std::string tables_error;
   int max_smem_optin = 0, sm_count = 0;
+  int schedule = 0;               // 0 auto, 1 static (ring-staged coalesced samples), 2 dynamic (lanes claim trajectories)
+  bool dynamic_last = false;
   bool x_nonneg = true;           // every count uploaded so far was >= 0 (large specialised kernels need it)
   rb_u32* d_gtab = nullptr;       // large specialised kernels: reaction records + saved-species list
   size_t gtab_capacity = 0;       // words
@@ -292,6 +294,16 @@ extern "C" int rebop_batch_set_rates(rebop_batch* b, const double* k, size_t n_r
   if (!b->tables_ok) b->tables_error = rebop_b200_last_error();
   return REBOP_OK;
 }
+extern "C" int rebop_batch_set_schedule(rebop_batch* b, int schedule) {
+  if (!b || schedule < 0 || schedule > 2) return rb_fail(REBOP_ERR_INVALID, "schedule must be 0 (auto), 1 (static) or 2 (dynamic)");
+  b->schedule = schedule;
+  return REBOP_OK;
+}
+extern "C" int rebop_batch_get_schedule(const rebop_batch* b, int* schedule_used) {
+  if (!b || !schedule_used) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  *schedule_used = b->dynamic_last ? 2 : 1;
+  return REBOP_OK;
+}
 extern "C" int rebop_batch_set_max_iters(rebop_batch* b, uint32_t max_iters) {
   if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   b->max_iters = max_iters;
@@ -402,6 +414,13 @@ static unsigned choose_ring_depth(const rebop_batch* b, unsigned block, unsigned
   return std::min(depth, cap);
 }
 
+// Auto schedule: claim trajectories dynamically unless the whole ensemble is resident at once anyway.
+static bool rb_auto_dynamic(const rebop_batch* b, unsigned n_save, unsigned n_points) {
+  (void)n_save;
+  (void)n_points;
+  return b->n > (size_t)b->sm_count * 2048u / 2u;
+}
+
 static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_first, uint32_t step_last,
                   int* d_out, uint32_t n_save, const uint32_t* save_idx) {
   const uint32_t S = b->net.n_species;
@@ -431,6 +450,16 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   const unsigned n_points = step_last - step_first + 1;
 
   RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
+
+  // --- schedule: dynamic when asked for, or (auto) when there are more trajectories than resident lanes
+  // and samples are sparse enough that uncoalesced sample stores do not matter
+  int schedule = b->schedule;
+  if (const char* env = std::getenv("REBOP_B200_SCHEDULE")) {
+    if (!std::strcmp(env, "static")) schedule = 1;
+    if (!std::strcmp(env, "dynamic")) schedule = 2;
+  }
+  const bool want_dynamic = schedule == 2 || (schedule == 0 && rb_auto_dynamic(b, p.n_save, n_points));
+  p.work_next = reinterpret_cast<rb_u32*>(b->d_counters + 3);
 
   // --- pick the kernel: build-time specialised, else NVRTC-specialised, else table-driven ---
   RbJitKernel jit;
@@ -503,11 +532,19 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
       RB_CUDA(cudaMemcpyAsync(b->d_gtab, b->h_gtab.data(), b->h_gtab.size() * sizeof(rb_u32), cudaMemcpyHostToDevice, b->stream));
       p.gtab = b->d_gtab;
     }
-    p.ring_depth = choose_ring_depth(b, block, jit.net_words + jit.static_smem / 4u, p.n_save, n_points, ctas);
+    p.ring_depth = want_dynamic ? 0u : choose_ring_depth(b, block, jit.net_words + jit.static_smem / 4u, p.n_save, n_points, ctas);
     const size_t smem = RB_SSA_SMEM_BYTES(jit.net_words, block, p.ring_depth, p.n_save);
     if (smem + RB_STATIC_SMEM_BYTES + jit.static_smem > (size_t)b->max_smem_optin)
       return rb_fail(REBOP_ERR_LIMIT, "specialised kernel: species state does not fit in shared memory");
-    const unsigned grid = (unsigned)((b->n + block - 1) / block);
+    unsigned grid = (unsigned)((b->n + block - 1) / block);
+    if (want_dynamic) {
+      int resident = 0;
+      int st = rb_jit_occupancy(jit, smem, &resident);
+      if (st) return st;
+      grid = std::min(grid, (unsigned)std::max(1, resident) * (unsigned)b->sm_count);
+      p.dynamic = 1;
+      p.n_launched = grid * block;
+    }
     int st = rb_jit_launch(jit, p, grid, smem, b->stream);
     if (st) return st;
     b->kernel_used = jit_kind;
@@ -517,11 +554,18 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     for (uint32_t j = 0; j < p.n_save; ++j) b->tables.save_idx[j] = (unsigned short)save_idx[j];
     const unsigned block = RB_TABLE_BLOCK;
     const unsigned net_words = S * block;
-    p.ring_depth = choose_ring_depth(b, block, net_words, p.n_save, n_points, 8);
+    p.ring_depth = want_dynamic ? 0u : choose_ring_depth(b, block, net_words, p.n_save, n_points, 8);
     const size_t smem = RB_SSA_SMEM_BYTES(net_words, block, p.ring_depth, p.n_save);
     if (smem + RB_STATIC_SMEM_BYTES > (size_t)b->max_smem_optin)
       return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: species state and sample ring do not fit in shared memory");
-    const unsigned grid = (unsigned)((b->n + block - 1) / block);
+    unsigned grid = (unsigned)((b->n + block - 1) / block);
+    if (want_dynamic) {
+      int resident = 0;
+      RB_CUDA(rb_table_occupancy(smem, &resident));
+      grid = std::min(grid, (unsigned)std::max(1, resident) * (unsigned)b->sm_count);
+      p.dynamic = 1;
+      p.n_launched = grid * block;
+    }
     RB_CUDA(rb_table_launch(&b->tables, p, grid, smem, b->stream));
     b->kernel_used = REBOP_KERNEL_TABLE;
   }
@@ -532,6 +576,7 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   RB_CUDA(cudaMemcpyAsync(counters, b->d_counters, sizeof counters, cudaMemcpyDeviceToHost, b->stream));
   RB_CUDA(cudaStreamSynchronize(b->stream));
   RB_CUDA(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
+  b->dynamic_last = p.dynamic != 0;
   b->seed_mode = 0;  // streams are live on the device from now on
   b->events_last = counters[0];
   b->lane_slots_last = counters[2];

@@ -234,6 +234,14 @@ extern "C" int rebop_network_jit_cubin(const rebop_network* net, char* buf, size
   return copy_out(cubin.data(), cubin.size(), buf, cap, needed);
 }
 
+int rb_jit_occupancy(const RbJitKernel& k, size_t smem_bytes, int* ctas_per_sm) {
+  cudaError_t err = cudaFuncSetAttribute(k.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k.kernel, (int)k.block, smem_bytes);
+  if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaOccupancyMaxActiveBlocksPerMultiprocessor: ") + cudaGetErrorString(err));
+  return REBOP_OK;
+}
+
 int rb_jit_launch(const RbJitKernel& k, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
                   cudaStream_t stream) {
   cudaError_t err = cudaFuncSetAttribute(k.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);

@@ -25,5 +25,7 @@ int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out);
 int rb_prebuilt_get(const rebop_network& net, RbJitKernel* out);
 // Source (and optionally the sm_100a cubin) of the specialised kernel; needs no GPU.
 int rb_jit_compile(const rebop_network& net, std::string* source, std::vector<char>* cubin);
+// Resident CTAs per SM of the kernel with this much dynamic shared memory.
+int rb_jit_occupancy(const RbJitKernel& k, size_t smem_bytes, int* ctas_per_sm);
 int rb_jit_launch(const RbJitKernel& k, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
                   cudaStream_t stream);

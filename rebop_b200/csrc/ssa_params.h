@@ -41,6 +41,9 @@ struct SsaRunParams {
   rb_u32 ring_depth;     // power of two, 1..32: grid points a warp can stage in shared memory
   rb_u32 seed_mode;      // 0 load rng, 1 seeds[], 2 seed_base + n
   rb_u32 max_iters;      // per-trajectory loop-iteration cap for this launch (0 = 2^32-1)
+  rb_u32 dynamic;        // 1: lanes claim further trajectories from *work_next when theirs is finished (ring_depth must be 0)
+  rb_u32 n_launched;     // dynamic: threads of the grid = trajectories assigned statically at the start
+  rb_u32* work_next;     // dynamic: [1] trajectories claimed beyond n_launched (zero before the launch)
   rb_u32 bias_hi;        // 0x43300000: high word of the biased-double species form (opaque to the compiler on purpose)
   // Constants the hot loop reads straight from the parameter bank (one LDCU.128 per pair) instead of
   // rebuilding them with two UMOVs each per iteration.

@@ -137,6 +137,12 @@ __global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel(const __gr
   rb_ssa_loop(net, p, rb_smem);
 }
 
+cudaError_t rb_table_occupancy(size_t smem_bytes, int* ctas_per_sm) {
+  cudaError_t err = cudaFuncSetAttribute(rb_ssa_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (err != cudaSuccess) return err;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, rb_ssa_table_kernel, RB_TABLE_BLOCK, smem_bytes);
+}
+
 cudaError_t rb_table_launch(const RbTables* host_tables, const SsaRunParams& p, unsigned grid,
                             size_t smem_bytes, cudaStream_t stream) {
   cudaError_t err = cudaMemcpyToSymbolAsync(c_tab, host_tables, sizeof(RbTables), 0,

@@ -12,3 +12,5 @@ struct SsaRunParams;
 // stay valid until the copy has been issued (pageable memory: the call returns after staging).
 cudaError_t rb_table_launch(const RbTables* host_tables, const SsaRunParams& p, unsigned grid,
                             size_t smem_bytes, cudaStream_t stream);
+// Resident CTAs per SM of the table-driven kernel with this much dynamic shared memory.
+cudaError_t rb_table_occupancy(size_t smem_bytes, int* ctas_per_sm);
