@@ -165,12 +165,14 @@ static std::string large_source(const rebop_network& net, const std::string& ker
   o << "    const rb_u32* save = p.gtab + " << R * 8 << ";\n";
   o << "    for (rb_u32 j = 0; j < p.n_save; ++j) dst[(size_t)j * stride] = __double2int_rn(xs[__ldg(save + j) * BLOCK]);\n";
   o << "  }\n};\n\n";
-  o << "extern \"C\" __global__ void __launch_bounds__(" << block << ", 2) " << kernel_name
-    << "(const __grid_constant__ SsaRunParams p) {\n";
-  o << "  extern __shared__ __align__(16) int rb_smem[];\n";
-  o << "  RbGenNet net;\n";
-  o << "  rb_ssa_loop(net, p, rb_smem);\n";
-  o << "}\n";
+  for (int dyn = 0; dyn < 2; ++dyn) {
+    o << "extern \"C\" __global__ void __launch_bounds__(" << block << ", 2) " << kernel_name << (dyn ? "_dyn" : "")
+      << "(const __grid_constant__ SsaRunParams p) {\n";
+    o << "  extern __shared__ __align__(16) int rb_smem[];\n";
+    o << "  RbGenNet net;\n";
+    o << "  rb_ssa_loop<RbGenNet, " << (dyn ? "true" : "false") << ">(net, p, rb_smem);\n";
+    o << "}\n";
+  }
   return o.str();
 }
 
@@ -373,13 +375,16 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   o << "    (void)row;\n  }\n";
   o << "};\n\n";
 
-  o << "extern \"C\" __global__ void __launch_bounds__(" << block;
-  if (minctas) o << ", " << minctas;
-  o << ") " << kernel_name
-    << "(const __grid_constant__ SsaRunParams p) {\n";
-  o << "  extern __shared__ __align__(16) int rb_smem[];\n";
-  o << "  RbGenNet net;\n";
-  o << "  rb_ssa_loop(net, p, rb_smem);\n";
-  o << "}\n";
+  // two entry points: static schedule (thread n runs trajectory n, ring-staged samples) and dynamic
+  // schedule (lanes claim trajectories), see rb_ssa_loop
+  for (int dyn = 0; dyn < 2; ++dyn) {
+    o << "extern \"C\" __global__ void __launch_bounds__(" << block;
+    if (minctas) o << ", " << minctas;
+    o << ") " << kernel_name << (dyn ? "_dyn" : "") << "(const __grid_constant__ SsaRunParams p) {\n";
+    o << "  extern __shared__ __align__(16) int rb_smem[];\n";
+    o << "  RbGenNet net;\n";
+    o << "  rb_ssa_loop<RbGenNet, " << (dyn ? "true" : "false") << ">(net, p, rb_smem);\n";
+    o << "}\n";
+  }
   return o.str();
 }

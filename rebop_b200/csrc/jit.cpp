@@ -117,6 +117,7 @@ int rb_prebuilt_get(const rebop_network& net, RbJitKernel* out) {
   const RbPrebuilt* e = rb_find_prebuilt(rb_codegen_source(net, "rb_ssa_jit", nullptr));
   if (!e) return rb_fail(REBOP_ERR_INVALID, "no build-time kernel was generated for this network (see rebop_b200/systems)");
   out->kernel = const_cast<void*>(e->kernel);
+  out->kernel_dyn = const_cast<void*>(e->kernel_dyn);
   out->block = e->block;
   out->net_words = e->net_words;
   out->static_smem = e->static_smem;
@@ -198,10 +199,12 @@ int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out) {
   CacheEntry e;
   cudaError_t err = cudaLibraryLoadData(&e.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(err));
-  cudaKernel_t kernel = nullptr;
+  cudaKernel_t kernel = nullptr, kernel_dyn = nullptr;
   err = cudaLibraryGetKernel(&kernel, e.lib, "rb_ssa_jit");
+  if (err == cudaSuccess) err = cudaLibraryGetKernel(&kernel_dyn, e.lib, "rb_ssa_jit_dyn");
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(err));
   e.k.kernel = kernel;
+  e.k.kernel_dyn = kernel_dyn;
   e.k.block = info.block;
   e.k.net_words = info.net_words;
   e.k.static_smem = info.static_smem;
@@ -234,20 +237,22 @@ extern "C" int rebop_network_jit_cubin(const rebop_network* net, char* buf, size
   return copy_out(cubin.data(), cubin.size(), buf, cap, needed);
 }
 
-int rb_jit_occupancy(const RbJitKernel& k, size_t smem_bytes, int* ctas_per_sm) {
-  cudaError_t err = cudaFuncSetAttribute(k.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+int rb_jit_occupancy(const RbJitKernel& k, bool dynamic, size_t smem_bytes, int* ctas_per_sm) {
+  void* kernel = dynamic ? k.kernel_dyn : k.kernel;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
-  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k.kernel, (int)k.block, smem_bytes);
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, (int)k.block, smem_bytes);
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaOccupancyMaxActiveBlocksPerMultiprocessor: ") + cudaGetErrorString(err));
   return REBOP_OK;
 }
 
-int rb_jit_launch(const RbJitKernel& k, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
+int rb_jit_launch(const RbJitKernel& k, bool dynamic, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
                   cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(k.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  void* kernel = dynamic ? k.kernel_dyn : k.kernel;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
   void* args[] = {const_cast<SsaRunParams*>(&p)};
-  err = cudaLaunchKernel(k.kernel, dim3(grid), dim3(k.block), args, smem_bytes, stream);
+  err = cudaLaunchKernel(kernel, dim3(grid), dim3(k.block), args, smem_bytes, stream);
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLaunchKernel: ") + cudaGetErrorString(err));
   return REBOP_OK;
 }

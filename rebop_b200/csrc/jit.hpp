@@ -10,7 +10,8 @@
 #include "ssa_params.h"
 
 struct RbJitKernel {
-  void* kernel = nullptr;  // cudaKernel_t
+  void* kernel = nullptr;      // cudaKernel_t / __global__ function: static schedule
+  void* kernel_dyn = nullptr;  // dynamic schedule
   unsigned block = 128;
   unsigned net_words = 0;
   unsigned static_smem = 0;  // bytes of static shared memory beyond the ensemble loop's own
@@ -26,6 +27,6 @@ int rb_prebuilt_get(const rebop_network& net, RbJitKernel* out);
 // Source (and optionally the sm_100a cubin) of the specialised kernel; needs no GPU.
 int rb_jit_compile(const rebop_network& net, std::string* source, std::vector<char>* cubin);
 // Resident CTAs per SM of the kernel with this much dynamic shared memory.
-int rb_jit_occupancy(const RbJitKernel& k, size_t smem_bytes, int* ctas_per_sm);
-int rb_jit_launch(const RbJitKernel& k, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
+int rb_jit_occupancy(const RbJitKernel& k, bool dynamic, size_t smem_bytes, int* ctas_per_sm);
+int rb_jit_launch(const RbJitKernel& k, bool dynamic, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
                   cudaStream_t stream);

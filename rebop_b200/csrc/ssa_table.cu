@@ -134,23 +134,29 @@ struct RbTableNet {
 __global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel(const __grid_constant__ SsaRunParams p) {
   extern __shared__ __align__(16) int rb_smem[];
   RbTableNet net;
-  rb_ssa_loop(net, p, rb_smem);
+  rb_ssa_loop<RbTableNet, false>(net, p, rb_smem);
+}
+__global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel_dyn(const __grid_constant__ SsaRunParams p) {
+  extern __shared__ __align__(16) int rb_smem[];
+  RbTableNet net;
+  rb_ssa_loop<RbTableNet, true>(net, p, rb_smem);
 }
 
-cudaError_t rb_table_occupancy(size_t smem_bytes, int* ctas_per_sm) {
-  cudaError_t err = cudaFuncSetAttribute(rb_ssa_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+cudaError_t rb_table_occupancy(bool dynamic, size_t smem_bytes, int* ctas_per_sm) {
+  auto kernel = dynamic ? rb_ssa_table_kernel_dyn : rb_ssa_table_kernel;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (err != cudaSuccess) return err;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, rb_ssa_table_kernel, RB_TABLE_BLOCK, smem_bytes);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, RB_TABLE_BLOCK, smem_bytes);
 }
 
-cudaError_t rb_table_launch(const RbTables* host_tables, const SsaRunParams& p, unsigned grid,
+cudaError_t rb_table_launch(const RbTables* host_tables, bool dynamic, const SsaRunParams& p, unsigned grid,
                             size_t smem_bytes, cudaStream_t stream) {
+  auto kernel = dynamic ? rb_ssa_table_kernel_dyn : rb_ssa_table_kernel;
   cudaError_t err = cudaMemcpyToSymbolAsync(c_tab, host_tables, sizeof(RbTables), 0,
                                             cudaMemcpyHostToDevice, stream);
   if (err != cudaSuccess) return err;
-  err = cudaFuncSetAttribute(rb_ssa_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem_bytes);
+  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (err != cudaSuccess) return err;
-  rb_ssa_table_kernel<<<grid, RB_TABLE_BLOCK, smem_bytes, stream>>>(p);
+  kernel<<<grid, RB_TABLE_BLOCK, smem_bytes, stream>>>(p);
   return cudaGetLastError();
 }

@@ -10,7 +10,7 @@ struct SsaRunParams;
 
 // Uploads the tables to __constant__ memory on `stream`, then launches.  The host image must
 // stay valid until the copy has been issued (pageable memory: the call returns after staging).
-cudaError_t rb_table_launch(const RbTables* host_tables, const SsaRunParams& p, unsigned grid,
+cudaError_t rb_table_launch(const RbTables* host_tables, bool dynamic, const SsaRunParams& p, unsigned grid,
                             size_t smem_bytes, cudaStream_t stream);
 // Resident CTAs per SM of the table-driven kernel with this much dynamic shared memory.
-cudaError_t rb_table_occupancy(size_t smem_bytes, int* ctas_per_sm);
+cudaError_t rb_table_occupancy(bool dynamic, size_t smem_bytes, int* ctas_per_sm);

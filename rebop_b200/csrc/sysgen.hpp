@@ -35,7 +35,8 @@ int rb_system_network(const rebop_system& sys, const double* params, size_t n_pa
 // source text the run-time generator would produce for the same network.
 struct RbPrebuilt {
   const char* key;      // rb_codegen_source(net, "rb_ssa_jit") of the network it was generated from
-  const void* kernel;   // __global__ function
+  const void* kernel;   // __global__ function, static schedule
+  const void* kernel_dyn;  // dynamic schedule
   unsigned block, static_smem, net_words;
   const char* name;     // system name
 };
