@@ -416,6 +416,48 @@ static unsigned choose_ring_depth(const rebop_batch* b, unsigned block, unsigned
   return std::min(depth, cap);
 }
 
+// Reaction records (see ssa_params.h) + saved-species list, rebuilt and uploaded per launch (rate constants
+// may have changed).
+static int upload_gtab(rebop_batch* b, const uint32_t* save_idx, uint32_t n_save) {
+  const uint32_t S = b->net.n_species;
+  const size_t R = b->net.rx.size();
+  b->h_gtab.assign(R * RB_GTAB_WORDS_PER_REACTION + std::max<uint32_t>(n_save, 1), 0u);
+  for (size_t r = 0; r < R; ++r) {
+    const RbReaction& rx = b->net.rx[r];
+    rb_u32* w = b->h_gtab.data() + r * RB_GTAB_WORDS_PER_REACTION;
+    std::memcpy(w, &rx.k, 8);
+    const size_t nt = rx.term_idx.size();
+    bool record = !rx.is_expr && nt <= 2;
+    for (size_t j = 0; j < nt; ++j) record = record && rx.term_idx[j] <= 0xffffu && rx.term_exp[j] <= 0xffu;
+    if (record) {
+      w[2] = (nt > 0 ? rx.term_idx[0] : 0u) | ((nt > 1 ? rx.term_idx[1] : 0u) << 16);
+      w[3] = (nt > 0 ? rx.term_exp[0] : 0u) | ((nt > 1 ? rx.term_exp[1] : 0u) << 8) | ((rb_u32)nt << 16);
+    } else {
+      w[3] = 0xffu << 16;
+    }
+    unsigned q = 0;
+    for (uint32_t sp = 0; sp < S; ++sp) {
+      if (rx.diff[sp] == 0) continue;
+      if (q < 4) {
+        w[4 + q / 2] |= sp << (16 * (q & 1));
+        w[6 + q / 2] |= ((rb_u32)(uint16_t)(int16_t)rx.diff[sp]) << (16 * (q & 1));
+      }
+      ++q;
+    }
+    if (q > 4) w[3] |= 1u << 24;
+  }
+  for (uint32_t j = 0; j < n_save; ++j) b->h_gtab[R * RB_GTAB_WORDS_PER_REACTION + j] = save_idx[j];
+  if (b->h_gtab.size() > b->gtab_capacity) {
+    if (b->d_gtab) RB_CUDA(cudaFree(b->d_gtab));
+    b->d_gtab = nullptr;
+    b->gtab_capacity = 0;
+    RB_CUDA(cudaMalloc(&b->d_gtab, b->h_gtab.size() * sizeof(rb_u32)));
+    b->gtab_capacity = b->h_gtab.size();
+  }
+  RB_CUDA(cudaMemcpyAsync(b->d_gtab, b->h_gtab.data(), b->h_gtab.size() * sizeof(rb_u32), cudaMemcpyHostToDevice, b->stream));
+  return REBOP_OK;
+}
+
 // Auto schedule.  Dynamic claiming pays when trajectories are long compared with the samples they emit
 // (no lane idles behind the slowest trajectory of its warp); the static schedule pays when samples are
 // dense (ring-staged, coalesced rows).  The number of events is not known in advance; the total
@@ -519,33 +561,8 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     unsigned ctas = std::max(1u, 2048u / block / 2u);
     if (jit.large) {
       ctas = 2;
-      // reaction records (see ssa_params.h) + saved-species list
-      const size_t R = b->net.rx.size();
-      b->h_gtab.assign(R * RB_GTAB_WORDS_PER_REACTION + std::max<uint32_t>(p.n_save, 1), 0u);
-      for (size_t r = 0; r < R; ++r) {
-        const RbReaction& rx = b->net.rx[r];
-        rb_u32* w = b->h_gtab.data() + r * RB_GTAB_WORDS_PER_REACTION;
-        std::memcpy(w, &rx.k, 8);
-        const size_t nt = rx.term_idx.size();
-        w[2] = (nt > 0 ? rx.term_idx[0] : 0u) | ((nt > 1 ? rx.term_idx[1] : 0u) << 16);
-        w[3] = (nt > 0 ? rx.term_exp[0] : 0u) | ((nt > 1 ? rx.term_exp[1] : 0u) << 8) | ((rb_u32)nt << 16);
-        unsigned q = 0;
-        for (uint32_t sp = 0; sp < S && q < 4; ++sp) {
-          if (rx.diff[sp] == 0) continue;
-          w[4 + q / 2] |= sp << (16 * (q & 1));
-          w[6 + q / 2] |= ((rb_u32)(uint16_t)(int16_t)rx.diff[sp]) << (16 * (q & 1));
-          ++q;
-        }
-      }
-      for (uint32_t j = 0; j < p.n_save; ++j) b->h_gtab[R * RB_GTAB_WORDS_PER_REACTION + j] = save_idx[j];
-      if (b->h_gtab.size() > b->gtab_capacity) {
-        if (b->d_gtab) RB_CUDA(cudaFree(b->d_gtab));
-        b->d_gtab = nullptr;
-        b->gtab_capacity = 0;
-        RB_CUDA(cudaMalloc(&b->d_gtab, b->h_gtab.size() * sizeof(rb_u32)));
-        b->gtab_capacity = b->h_gtab.size();
-      }
-      RB_CUDA(cudaMemcpyAsync(b->d_gtab, b->h_gtab.data(), b->h_gtab.size() * sizeof(rb_u32), cudaMemcpyHostToDevice, b->stream));
+      int st = upload_gtab(b, save_idx, p.n_save);
+      if (st) return st;
       p.gtab = b->d_gtab;
     }
     p.ring_depth = want_dynamic ? 0u : choose_ring_depth(b, block, jit.net_words + jit.static_smem / 4u, p.n_save, n_points, ctas);
@@ -568,6 +585,11 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     if (!b->tables_ok) return rb_fail(REBOP_ERR_LIMIT, b->tables_error);
     if (p.n_save > RB_TAB_MAX_SAVE) return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: more than 1024 saved species");
     for (uint32_t j = 0; j < p.n_save; ++j) b->tables.save_idx[j] = (unsigned short)save_idx[j];
+    {
+      int st = upload_gtab(b, save_idx, p.n_save);
+      if (st) return st;
+      p.gtab = b->d_gtab;
+    }
     const unsigned block = RB_TABLE_BLOCK;
     const unsigned net_words = S * block;
     p.ring_depth = want_dynamic ? 0u : choose_ring_depth(b, block, net_words, p.n_save, n_points, 8);

@@ -15,7 +15,8 @@ typedef unsigned int rb_u32;
 
 // Record of one reaction in SsaRunParams::gtab (8 words, built by the engine at launch):
 //   w0,w1  rate constant (f64)            w2  species of term 0 | species of term 1 << 16
-//   w3     exponent 0 | exponent 1 << 8 | number of terms << 16
+//   w3     exponent 0 | exponent 1 << 8 | number of terms << 16 | (more than four species change) << 24
+//          number of terms = 0xff: not a record reaction (expression rate or more than two terms)
 //   w4,w5  jump species 0..3 (u16 each)   w6,w7  jump differences 0..3 (i16 each, 0 = unused)
 // followed, after the last reaction, by the saved-species list (one word each).
 #define RB_GTAB_WORDS_PER_REACTION 8
@@ -51,7 +52,7 @@ struct SsaRunParams {
   double one_m_eps;      // 1 - 2^-53
   int byte_sel[4];       // dp4a selectors 1, 1<<8, 1<<16, 1<<24
   rb_u64 save_mask[2];   // specialised kernels: bit s set => species s is sampled
-  const rb_u32* gtab;    // large specialised kernels: per-reaction records + saved-species list in global memory
+  const rb_u32* gtab;    // table-driven and large specialised kernels: per-reaction records (+ saved-species list)
   double k[RB_MAX_K];    // specialised kernels: rate constants (kernel parameters may be up to 32 KB on sm_70+)
 };
 

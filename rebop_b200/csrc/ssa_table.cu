@@ -68,61 +68,91 @@ struct RbTableNet {
     return stack[0];
   }
 
-  // Rate::rate for reaction r.
-  __device__ __forceinline__ double rate(int r) const {
+  // One reactant term: acc * n(n-1)...(n-e+1) in the arithmetic of the selected engine.
+  static __device__ __forceinline__ double term(double acc, int n, int e, int arith) {
+    if (e == 1) return __dmul_rn(acc, rb_i2d(n));
+    if (arith == 0) {
+      // src/gillespie.rs:73-87: factors (n+1-e)..=n ascending, one f64 multiply each
+      for (int f = n + 1 - e; f <= n; ++f) acc = __dmul_rn(acc, rb_i2d(f));
+      return acc;
+    }
+    // src/gillespie_macro.rs:133-146: wrapping integer falling factorial, one conversion
+    rb_u64 prod = (rb_u64)(rb_i64)n;
+    for (int i = 1; i < e; ++i) prod *= (rb_u64)(rb_i64)(n - i);
+    return __dmul_rn(acc, __ll2double_rn((rb_i64)prod));
+  }
+
+  // Rate::rate for reaction r through the CSR tables in constant memory (any number of terms, expressions).
+  __device__ __noinline__ double rate_general(int r) const {
     const int e0 = c_tab.expr_ptr[r], e1 = c_tab.expr_ptr[r + 1];
     if (e1 > e0) return eval_expr(e0, e1);
     double acc = c_tab.k[r];
     const int j1 = c_tab.term_ptr[r + 1];
-    for (int j = c_tab.term_ptr[r]; j < j1; ++j) {
-      const int n = xs[c_tab.term_idx[j] * BLOCK];
-      const int e = c_tab.term_exp[j];
-      if (e == 1) {
-        acc = __dmul_rn(acc, rb_i2d(n));
-      } else if (c_tab.arith == 0) {
-        // src/gillespie.rs:73-87: factors (n+1-e)..=n ascending, one f64 multiply each
-        for (int f = n + 1 - e; f <= n; ++f) acc = __dmul_rn(acc, rb_i2d(f));
-      } else {
-        // src/gillespie_macro.rs:133-146: wrapping integer falling factorial, one conversion
-        rb_u64 prod = (rb_u64)(rb_i64)n;
-        for (int i = 1; i < e; ++i) prod *= (rb_u64)(rb_i64)(n - i);
-        acc = __dmul_rn(acc, __ll2double_rn((rb_i64)prod));
-      }
-    }
+    for (int j = c_tab.term_ptr[r]; j < j1; ++j)
+      acc = term(acc, xs[c_tab.term_idx[j] * BLOCK], c_tab.term_exp[j], c_tab.arith);
+    return acc;
+  }
+
+  // Rate::rate for reaction r.  The common case -- mass action with at most two reactant terms -- is
+  // served by ONE 16-byte record (SsaRunParams::gtab, see ssa_params.h) read at a warp-uniform address,
+  // so consecutive reactions do not wait on chains of dependent table loads.
+  __device__ __forceinline__ double rate(const uint4* __restrict__ rec, int r) const {
+    const uint4 w = __ldg(rec + 2 * r);
+    const rb_u32 n = (w.w >> 16) & 0xffu;
+    if (n == 0xffu) return rate_general(r);
+    double acc = __hiloint2double((int)w.y, (int)w.x);
+    if (n >= 1u) acc = term(acc, xs[(w.z & 0xffffu) * BLOCK], (int)(w.w & 0xffu), c_tab.arith);
+    if (n >= 2u) acc = term(acc, xs[(w.z >> 16) * BLOCK], (int)((w.w >> 8) & 0xffu), c_tab.arith);
     return acc;
   }
 
   // make_cumrates (src/gillespie.rs:357-364); only the total is kept, fire() re-walks the sum.
-  __device__ __forceinline__ double propensities(const SsaRunParams&) const {
+  __device__ __forceinline__ double propensities(const SsaRunParams& p) const {
     const int R = c_tab.n_reactions;
+    const uint4* rec = reinterpret_cast<const uint4*>(p.gtab);
     double total = 0.0;
-    for (int r = 0; r < R; ++r) total = __dadd_rn(total, rate(r));
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) total = __dadd_rn(total, rate(rec, r));
     return total;
   }
 
-  __device__ __forceinline__ bool fire(const SsaRunParams&, double chosen) {
+  __device__ __forceinline__ bool fire(const SsaRunParams& p, double chosen) {
     const int R = c_tab.n_reactions;
+    const uint4* rec = reinterpret_cast<const uint4*>(p.gtab);
     double cum = 0.0;
     int i;
     if (c_tab.arith == 0) {
       // choose_cumrate_sum (src/gillespie.rs:402-407): the index is a count
       i = 0;
+#pragma unroll 4
       for (int r = 0; r < R; ++r) {
-        cum = __dadd_rn(cum, rate(r));
+        cum = __dadd_rn(cum, rate(rec, r));
         i += (cum < chosen) ? 1 : 0;
       }
       if (i >= R) i = R - 1;  // unreachable for finite totals (src/gillespie.rs:339)
     } else {
       // _choice! (src/gillespie_macro.rs:150-171): first r with chosen < carry + r_r
       i = R;
+#pragma unroll 4
       for (int r = 0; r < R; ++r) {
-        cum = __dadd_rn(cum, rate(r));
+        cum = __dadd_rn(cum, rate(rec, r));
         if (i == R && chosen < cum) i = r;
       }
       if (i == R) return false;
     }
-    const int j1 = c_tab.jump_ptr[i + 1];
-    for (int j = c_tab.jump_ptr[i]; j < j1; ++j) xs[c_tab.jump_idx[j] * BLOCK] += c_tab.jump_diff[j];
+    const uint4 j = __ldg(rec + 2 * i + 1);
+    if ((__ldg(rec + 2 * i).w >> 24) == 0u) {
+      // at most four species change: (species, difference) pairs from the record
+      const rb_u32 idx[4] = {j.x & 0xffffu, j.x >> 16, j.y & 0xffffu, j.y >> 16};
+      const int diff[4] = {(int)(short)(j.z & 0xffffu), (int)(short)(j.z >> 16), (int)(short)(j.w & 0xffffu),
+                           (int)(short)(j.w >> 16)};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (diff[q] != 0) xs[idx[q] * BLOCK] += diff[q];
+    } else {
+      const int j1 = c_tab.jump_ptr[i + 1];
+      for (int q = c_tab.jump_ptr[i]; q < j1; ++q) xs[c_tab.jump_idx[q] * BLOCK] += c_tab.jump_diff[q];
+    }
     return true;
   }
 
