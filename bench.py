@@ -375,7 +375,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-traj-per-core", type=int, default=1024, help="cpu_baseline sample size per host core")
-    ap.add_argument("--ref-traj-per-core", type=int, default=128, help="--impl reference: trajectories per core per step")
+    ap.add_argument("--ref-traj-per-core", type=int, default=512, help="--impl reference: trajectories per core per step")
     args = ap.parse_args()
 
     from rebop_b200 import models
