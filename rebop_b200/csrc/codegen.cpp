@@ -156,10 +156,14 @@ static std::string large_source(const rebop_network& net, const std::string& ker
     if (r % ckn == ckn - 1 || r == R - 1) o << "    ck[" << r / ckn << "] = c;\n";
   }
   o << "    return c;\n  }\n";
-  o << "  __device__ __forceinline__ bool fire(const SsaRunParams& p, double chosen) {\n";
-  if (R == 0) o << "    return false;\n";
-  else o << "    return rb_large_fire<" << nck << ", " << ckn << ", " << R << ", " << (macro ? "true" : "false")
+  o << "  __device__ __forceinline__ int select(const SsaRunParams& p, double chosen) const {\n";
+  if (R == 0) o << "    return 0;\n";
+  else o << "    return rb_large_select<" << nck << ", " << ckn << ", " << R << ", " << (macro ? "true" : "false")
          << ", BLOCK>(ck, chosen, xs, p.gtab);\n";
+  o << "  }\n";
+  o << "  __device__ __forceinline__ bool apply(const SsaRunParams& p, int pick) {\n";
+  if (R == 0) o << "    return false;\n";
+  else o << "    return rb_large_apply<" << R << ", BLOCK>(pick, xs, p.gtab);\n";
   o << "  }\n";
   o << "  __device__ __forceinline__ void record(const SsaRunParams& p, int* dst, rb_u32 stride) const {\n";
   o << "    const rb_u32* save = p.gtab + " << R * 8 << ";\n";
@@ -315,8 +319,10 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   o << "  }\n";
 
   // select + update
-  o << "  __device__ __forceinline__ bool fire(const SsaRunParams& p, double chosen) {\n";
+  o << "  __device__ __forceinline__ int select(const SsaRunParams&, double chosen) const {\n";
   if (R == 0) {
+    o << "    return 0;\n  }\n";
+    o << "  __device__ __forceinline__ bool apply(const SsaRunParams&, int) {\n";
     o << "    return false;\n";
   } else {
     if (!macro) {
@@ -337,8 +343,10 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
       }
       if (R % 2) o << "    rb_first_lt<0>(i, chosen, c[0]);\n";
       o << "    i = min(i, i2);\n";
-      o << "    if (i == " << R << ") return false;\n";
     }
+    o << "    return i;\n  }\n";
+    o << "  __device__ __forceinline__ bool apply(const SsaRunParams& p, int i) {\n";
+    if (macro) o << "    if (i == " << R << ") return false;\n";
     // fetch the packed stoichiometry row of reaction i from shared memory
     if (dwp == 1) {
       o << "    const int w0 = rb_lds_i32(tab + 4u * i);\n";

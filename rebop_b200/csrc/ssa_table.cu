@@ -116,7 +116,7 @@ struct RbTableNet {
     return total;
   }
 
-  __device__ __forceinline__ bool fire(const SsaRunParams& p, double chosen) {
+  __device__ __forceinline__ int select(const SsaRunParams& p, double chosen) const {
     const int R = c_tab.n_reactions;
     const uint4* rec = reinterpret_cast<const uint4*>(p.gtab);
     double cum = 0.0;
@@ -130,6 +130,7 @@ struct RbTableNet {
         i += (cum < chosen) ? 1 : 0;
       }
       if (i >= R) i = R - 1;  // unreachable for finite totals (src/gillespie.rs:339)
+      if (R == 0) i = 0;
     } else {
       // _choice! (src/gillespie_macro.rs:150-171): first r with chosen < carry + r_r
       i = R;
@@ -138,8 +139,13 @@ struct RbTableNet {
         cum = __dadd_rn(cum, rate(rec, r));
         if (i == R && chosen < cum) i = r;
       }
-      if (i == R) return false;
     }
+    return i;  // R: nothing matches (macro arithmetic), or no reactions at all
+  }
+
+  __device__ __forceinline__ bool apply(const SsaRunParams& p, int i) {
+    if (i >= c_tab.n_reactions) return false;
+    const uint4* rec = reinterpret_cast<const uint4*>(p.gtab);
     const uint4 j = __ldg(rec + 2 * i + 1);
     if ((__ldg(rec + 2 * i).w >> 24) == 0u) {
       // at most four species change: (species, difference) pairs from the record

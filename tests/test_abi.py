@@ -194,7 +194,7 @@ def test_large_network_gets_the_shared_memory_form(ffi):
     net = models.build_network(model)
     assert net.nb_reactions == 500
     src = net.codegen()
-    assert "large form" in src and "32 checkpoints of 16 reactions" in src and "rb_large_fire<32, 16, 500, false, BLOCK>" in src
+    assert "large form" in src and "32 checkpoints of 16 reactions" in src and "rb_large_select<32, 16, 500, false, BLOCK>" in src
     assert "static constexpr int BLOCK = 128;" in src
     cubin = net.jit_cubin()  # NVRTC, sm_100a, no GPU needed
     assert cubin[:4] == b"\x7fELF"
