@@ -315,6 +315,9 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
     if (r == 0) o << "    c[0] = " << a << ";\n";
     else o << "    c[" << r << "] = __dadd_rn(c[" << r - 1 << "], " << a << ");\n";
   }
+  // pin the cumulative rates: under register pressure the compiler otherwise re-computes some of them
+  // (FP64 pipe work) next to the comparisons of select()
+  for (int r = 0; r < R; ++r) o << "    asm volatile(\"\" : \"+d\"(c[" << r << "]));\n";
   if (R > 0) o << "    return c[" << R - 1 << "];\n";
   o << "  }\n";
 
