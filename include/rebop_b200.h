@@ -189,6 +189,10 @@ int rebop_batch_samples_device(const rebop_batch* b, const int32_t** dev_ptr, si
 /* Copy the last run_grid's samples to the host: int32 or int64, [step][save][trajectory]. */
 int rebop_batch_samples_host_i32(rebop_batch* b, int32_t* out);
 int rebop_batch_samples_host_i64(rebop_batch* b, int64_t* out);
+/* Same as _i32 into a wider host array: row r of this batch goes to out[r * ld .. r * ld + n_traj), so the
+ * shards of an ensemble (one batch per GPU) land side by side in one [step][save][all trajectories] array
+ * with no intermediate copy; out points at the first trajectory of this batch in row 0. */
+int rebop_batch_samples_host_i32_strided(rebop_batch* b, int32_t* out, size_t ld);
 /* K4: per (step, saved species) sum and sum of squares over the trajectories of this batch,
  * as exact integers (so that sums over GPUs are order-independent). sum, sumsq: [n_rows]. */
 int rebop_batch_sample_sums(rebop_batch* b, int64_t* sum, uint64_t* sumsq);

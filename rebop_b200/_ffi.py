@@ -100,6 +100,7 @@ SIGNATURES = {
     "rebop_batch_samples_device": (C.c_int, [_vp, C.POINTER(C.c_void_p), _szp, _u32p]),
     "rebop_batch_samples_host_i32": (C.c_int, [_vp, _i32p]),
     "rebop_batch_samples_host_i64": (C.c_int, [_vp, _i64p]),
+    "rebop_batch_samples_host_i32_strided": (C.c_int, [_vp, _i32p, C.c_size_t]),
     "rebop_batch_sample_sums": (C.c_int, [_vp, _i64p, _u64p]),
     "rebop_batch_sample_sums_device": (C.c_int, [_vp, C.POINTER(C.c_void_p), _u32p]),
     "rebop_batch_events": (C.c_int, [_vp, _u64p, _u64p]),
@@ -398,6 +399,15 @@ class Batch:
             else:
                 raise TypeError("dtype must be int32 or int64")
         return out
+
+    def samples_into(self, out: np.ndarray, first: int) -> None:
+        """Write the samples into columns [first, first + n_traj) of a C-contiguous int32 array
+        [nb_steps+1][n_save][n_total] (no intermediate copy)."""
+        assert out.dtype == np.int32 and out.flags.c_contiguous and out.ndim == 3
+        assert out.shape[0] * out.shape[1] == self.rows and first + self.n_traj <= out.shape[2]
+        if out.size:
+            base = out.ctypes.data + 4 * first
+            check(lib.rebop_batch_samples_host_i32_strided(self._h, C.cast(base, _i32p), out.shape[2]))
 
     def samples_device(self):
         """(device pointer, leading dimension in elements, rows) of the last run_grid's samples."""

@@ -685,6 +685,17 @@ extern "C" int rebop_batch_samples_host_i32(rebop_batch* b, int32_t* out) {
   return REBOP_OK;
 }
 
+extern "C" int rebop_batch_samples_host_i32_strided(rebop_batch* b, int32_t* out, size_t ld) {
+  if (!b || !out) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  if (ld < b->n) return rb_fail(REBOP_ERR_INVALID, "ld must be at least the number of trajectories of the batch");
+  if (b->out_rows == 0) return REBOP_OK;
+  RB_CUDA(cudaSetDevice(b->device));
+  RB_CUDA(cudaMemcpy2DAsync(out, ld * sizeof(int), b->d_out, b->ldn * sizeof(int), b->n * sizeof(int),
+                            b->out_rows, cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  return REBOP_OK;
+}
+
 extern "C" int rebop_batch_samples_host_i64(rebop_batch* b, int64_t* out) {
   if (!b || !out) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   const size_t count = (size_t)b->out_rows * b->n;

@@ -99,7 +99,7 @@ def run_sharded(net: "_ffi.Network", n_total: int, x0, seeds, tmax: float, nb_st
             try:
                 b.run_grid(tmax, nb_steps, save_idx=save_idx)
                 if want_samples and rows:
-                    out[:, :, lo:lo + cnt] = b.samples()
+                    b.samples_into(out, lo)  # straight into this shard's columns of the result
                 s1, s2 = b.sample_sums() if rows else (np.zeros(0, np.int64), np.zeros(0, np.uint64))
                 results[i] = (s1, s2, b.events()[1], b.last_kernel_ms)
             finally:
