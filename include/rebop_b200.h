@@ -183,6 +183,15 @@ int rebop_batch_advance_until(rebop_batch* b, double tmax);
  * densely as [step][save][trajectory]. */
 int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
                          uint32_t n_save, int32_t* host_out);
+/* The nb_steps = 0 path of the binding (src/pyo3_gillespie.rs:209-223) for every trajectory:
+ * record; while t < tmax { _advance_one_reaction (src/gillespie.rs:275-297); record } -- one row per applied
+ * reaction, the last one at or beyond tmax (t = +inf when the state became absorbing).  The log stays on the
+ * device: times f64 [total_rows], samples int32 [n_save][total_rows]; trajectory n owns rows
+ * offsets[n] .. offsets[n+1].  Needs fewer than 2^32 rows in total. */
+int rebop_batch_run_events(rebop_batch* b, double tmax, const uint32_t* save_idx, uint32_t n_save);
+int rebop_batch_events_log_size(const rebop_batch* b, uint64_t* total_rows, uint32_t* n_save);
+/* offsets: [n_traj + 1], times: [total_rows], samples: [n_save][total_rows]; any of them may be NULL. */
+int rebop_batch_events_log_host(rebop_batch* b, uint64_t* offsets, double* times, int32_t* samples);
 /* Device view of the last run_grid's samples. */
 int rebop_batch_samples_device(const rebop_batch* b, const int32_t** dev_ptr, size_t* ld,
                                uint32_t* n_rows);

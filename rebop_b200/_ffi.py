@@ -97,6 +97,9 @@ SIGNATURES = {
     "rebop_batch_set_species": (C.c_int, [_vp, _i64p, C.c_int]),
     "rebop_batch_advance_until": (C.c_int, [_vp, C.c_double]),
     "rebop_batch_run_grid": (C.c_int, [_vp, C.c_double, C.c_uint32, _u32p, C.c_uint32, _i32p]),
+    "rebop_batch_run_events": (C.c_int, [_vp, C.c_double, _u32p, C.c_uint32]),
+    "rebop_batch_events_log_size": (C.c_int, [_vp, _u64p, _u32p]),
+    "rebop_batch_events_log_host": (C.c_int, [_vp, _u64p, _f64p, _i32p]),
     "rebop_batch_samples_device": (C.c_int, [_vp, C.POINTER(C.c_void_p), _szp, _u32p]),
     "rebop_batch_samples_host_i32": (C.c_int, [_vp, _i32p]),
     "rebop_batch_samples_host_i64": (C.c_int, [_vp, _i64p]),
@@ -399,6 +402,25 @@ class Batch:
             else:
                 raise TypeError("dtype must be int32 or int64")
         return out
+
+    def run_events(self, tmax: float, save_idx=None):
+        """nb_steps = 0: one row per applied reaction.  Returns (offsets [n+1], times [rows], samples [n_save][rows]);
+        trajectory n owns rows offsets[n]:offsets[n+1]."""
+        n_save = self.net.n_species if save_idx is None else len(save_idx)
+        sp = None
+        if save_idx is not None:
+            sv = np.ascontiguousarray(save_idx, dtype=np.uint32)
+            sp = ptr(sv, C.c_uint32)
+        check(lib.rebop_batch_run_events(self._h, float(tmax), sp, n_save))
+        total, ns = C.c_uint64(), C.c_uint32()
+        check(lib.rebop_batch_events_log_size(self._h, C.byref(total), C.byref(ns)))
+        offsets = np.empty(self.n_traj + 1, dtype=np.uint64)
+        times = np.empty(total.value, dtype=np.float64)
+        samples = np.empty((ns.value, total.value), dtype=np.int32)
+        check(lib.rebop_batch_events_log_host(self._h, ptr(offsets, C.c_uint64), ptr(times, C.c_double) if times.size else None,
+                                              ptr(samples, C.c_int32) if samples.size else None))
+        self.rows = 0
+        return offsets, times, samples
 
     def samples_into(self, out: np.ndarray, first: int) -> None:
         """Write the samples into columns [first, first + n_traj) of a C-contiguous int32 array

@@ -58,6 +58,28 @@ std::string emit_expr(const std::vector<rebop_expr_op>& prog) {
 
 }  // namespace
 
+// Entry points of a generated translation unit.  RB_VARIANT_GRID: static and dynamic schedule of the
+// time-grid loop; RB_VARIANT_EVENTS: counting and writing pass of the event-log mode.
+static void emit_kernels(std::ostringstream& o, const std::string& kernel_name, unsigned block, unsigned minctas, int variant) {
+  struct Entry { const char* suffix; const char* body; int in; };
+  const Entry entries[] = {
+      {"", "rb_ssa_loop<RbGenNet, false>(net, p, rb_smem);", RB_VARIANT_GRID},
+      {"_dyn", "rb_ssa_loop<RbGenNet, true>(net, p, rb_smem);", RB_VARIANT_GRID},
+      {"_evc", "rb_ssa_events<RbGenNet, false>(net, p, rb_smem);", RB_VARIANT_EVENTS},
+      {"_evw", "rb_ssa_events<RbGenNet, true>(net, p, rb_smem);", RB_VARIANT_EVENTS},
+  };
+  for (const Entry& e : entries) {
+    if (!(variant & e.in)) continue;
+    o << "extern \"C\" __global__ void __launch_bounds__(" << block;
+    if (minctas) o << ", " << minctas;
+    o << ") " << kernel_name << e.suffix << "(const __grid_constant__ SsaRunParams p) {\n";
+    o << "  extern __shared__ __align__(16) int rb_smem[];\n";
+    o << "  RbGenNet net;\n";
+    o << "  " << e.body << "\n";
+    o << "}\n";
+  }
+}
+
 static bool small_form_ok(const rebop_network& net) {
   return net.n_species <= RB_GEN_MAX_SPECIES && net.rx.size() <= RB_GEN_MAX_REACTIONS;
 }
@@ -98,7 +120,7 @@ bool rb_codegen_supported(const rebop_network& net, std::string* why) {
 
 bool rb_codegen_is_large(const rebop_network& net) { return !small_form_ok(net); }
 
-static std::string large_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info) {
+static std::string large_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info, int variant) {
   const int S = (int)net.n_species;
   const int R = (int)net.rx.size();
   const bool macro = net.arith == REBOP_ARITH_MACRO;
@@ -169,19 +191,12 @@ static std::string large_source(const rebop_network& net, const std::string& ker
   o << "    const rb_u32* save = p.gtab + " << R * 8 << ";\n";
   o << "    for (rb_u32 j = 0; j < p.n_save; ++j) dst[(size_t)j * stride] = __double2int_rn(xs[__ldg(save + j) * BLOCK]);\n";
   o << "  }\n};\n\n";
-  for (int dyn = 0; dyn < 2; ++dyn) {
-    o << "extern \"C\" __global__ void __launch_bounds__(" << block << ", 2) " << kernel_name << (dyn ? "_dyn" : "")
-      << "(const __grid_constant__ SsaRunParams p) {\n";
-    o << "  extern __shared__ __align__(16) int rb_smem[];\n";
-    o << "  RbGenNet net;\n";
-    o << "  rb_ssa_loop<RbGenNet, " << (dyn ? "true" : "false") << ">(net, p, rb_smem);\n";
-    o << "}\n";
-  }
+  emit_kernels(o, kernel_name, block, 2, variant);
   return o.str();
 }
 
-std::string rb_codegen_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info) {
-  if (!small_form_ok(net)) return large_source(net, kernel_name, info);
+std::string rb_codegen_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info, int variant) {
+  if (!small_form_ok(net)) return large_source(net, kernel_name, info, variant);
   const int S = (int)net.n_species;
   const int R = (int)net.rx.size();
   const bool macro = net.arith == REBOP_ARITH_MACRO;
@@ -386,16 +401,6 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   o << "    (void)row;\n  }\n";
   o << "};\n\n";
 
-  // two entry points: static schedule (thread n runs trajectory n, ring-staged samples) and dynamic
-  // schedule (lanes claim trajectories), see rb_ssa_loop
-  for (int dyn = 0; dyn < 2; ++dyn) {
-    o << "extern \"C\" __global__ void __launch_bounds__(" << block;
-    if (minctas) o << ", " << minctas;
-    o << ") " << kernel_name << (dyn ? "_dyn" : "") << "(const __grid_constant__ SsaRunParams p) {\n";
-    o << "  extern __shared__ __align__(16) int rb_smem[];\n";
-    o << "  RbGenNet net;\n";
-    o << "  rb_ssa_loop<RbGenNet, " << (dyn ? "true" : "false") << ">(net, p, rb_smem);\n";
-    o << "}\n";
-  }
+  emit_kernels(o, kernel_name, block, minctas, variant);
   return o.str();
 }

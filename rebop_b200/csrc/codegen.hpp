@@ -23,4 +23,9 @@ bool rb_codegen_supported(const rebop_network& net, std::string* why);
 // True when the network gets the large form (state in shared memory) instead of register-resident state.
 bool rb_codegen_is_large(const rebop_network& net);
 // Source text of `extern "C" __global__ void <kernel_name>(SsaRunParams)`; includes "ssa_kernel.cuh".
-std::string rb_codegen_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info);
+// `variant` selects the entry points: the time-grid kernels <name>, <name>_dyn and/or the event-log kernels
+// <name>_evc, <name>_evw.  The grid variant of "rb_ssa_jit" is the text build-time kernels are registered under.
+#define RB_VARIANT_GRID 1
+#define RB_VARIANT_EVENTS 2
+std::string rb_codegen_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info,
+                              int variant = RB_VARIANT_GRID);

@@ -64,6 +64,13 @@ struct rebop_batch {
   rb_u32* d_gtab = nullptr;       // large specialised kernels: reaction records + saved-species list
   size_t gtab_capacity = 0;       // words
   std::vector<rb_u32> h_gtab;
+  // event-log mode (nb_steps = 0)
+  rb_u32* d_ev_counts = nullptr;
+  rb_u64* d_ev_offsets = nullptr;
+  double* d_ev_times = nullptr;
+  size_t ev_times_capacity = 0;
+  std::vector<uint64_t> ev_offsets;  // [n + 1] after run_events
+  uint32_t ev_n_save = 0;
 };
 
 // ---------------------------------------------------------------------------
@@ -220,6 +227,7 @@ extern "C" void rebop_batch_destroy(rebop_batch* b) {
   if (b->own_stream && b->own_stream != b->stream) cudaStreamSynchronize(b->own_stream);
   cudaFree(b->d_x); cudaFree(b->d_t); cudaFree(b->d_rng); cudaFree(b->d_seeds);
   cudaFree(b->d_out); cudaFree(b->d_counters); cudaFree(b->d_sums); cudaFree(b->d_gtab);
+  cudaFree(b->d_ev_counts); cudaFree(b->d_ev_offsets); cudaFree(b->d_ev_times);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->own_stream) cudaStreamDestroy(b->own_stream);
@@ -479,32 +487,74 @@ static bool rb_auto_dynamic(const rebop_batch* b, double tmax, unsigned n_save, 
   return a0 * tmax >= (double)n_save * n_points;
 }
 
+static void fill_params(const rebop_batch* b, SsaRunParams* p) {
+  std::memset(p, 0, sizeof *p);
+  p->x = b->d_x;
+  p->t = b->d_t;
+  p->rng = b->d_rng;
+  p->seeds = b->d_seeds;
+  p->seed_base = b->seed_base;
+  p->events = b->d_counters;
+  p->status = reinterpret_cast<rb_u32*>(b->d_counters + 1);
+  p->work_next = reinterpret_cast<rb_u32*>(b->d_counters + 3);
+  p->n_traj = (rb_u32)b->n;
+  p->ldn = (rb_u32)b->ldn;
+  p->seed_mode = b->seed_mode;
+  p->max_iters = b->max_iters;
+  p->bias_hi = 0x43300000u;
+  p->bias = 0x1.0p52 + 0x1.0p31;
+  p->one_m_eps = 1.0 - 0x1.0p-53;
+  for (int l = 0; l < 4; ++l) p->byte_sel[l] = 1 << (8 * l);
+  for (size_t r = 0; r < b->net.rx.size() && r < RB_MAX_K; ++r) p->k[r] = b->net.rx[r].k;
+}
+
+// Build-time specialised, else NVRTC-specialised, else table-driven (use_jit = false).  `events` asks
+// for the event-log entry points instead of the time-grid ones.
+static int pick_kernel(rebop_batch* b, bool events, RbJitKernel* jit, bool* use_jit, int* jit_kind) {
+  *use_jit = false;
+  *jit_kind = REBOP_KERNEL_NVRTC;
+  if (b->kernel_pref == REBOP_KERNEL_AUTO || b->kernel_pref == REBOP_KERNEL_PREBUILT) {
+    int st = rb_prebuilt_get(b->net, jit);
+    if (st == REBOP_OK) {
+      *use_jit = true;
+      *jit_kind = REBOP_KERNEL_PREBUILT;
+    } else if (b->kernel_pref == REBOP_KERNEL_PREBUILT) {
+      return st;
+    }
+  }
+  if (!*use_jit && (b->kernel_pref == REBOP_KERNEL_AUTO || b->kernel_pref == REBOP_KERNEL_NVRTC)) {
+    int st = events ? rb_jit_get_events(b->net, b->device, jit) : rb_jit_get(b->net, b->device, jit);
+    if (st == REBOP_OK) {
+      *use_jit = true;
+    } else if (b->kernel_pref == REBOP_KERNEL_NVRTC) {
+      return st;
+    }
+  }
+  // large specialised kernels assume non-decreasing cumulative rates: k >= 0 and counts >= 0
+  if (*use_jit && jit->large) {
+    bool ok = b->x_nonneg;
+    for (const RbReaction& rx : b->net.rx) ok = ok && !(rx.k < 0.0);
+    if (!ok) {
+      if (b->kernel_pref != REBOP_KERNEL_AUTO)
+        return rb_fail(REBOP_ERR_LIMIT, "the specialised kernel for large networks needs rate constants >= 0 and counts >= 0");
+      *use_jit = false;
+    }
+  }
+  if (!*use_jit && !b->tables_ok) return rb_fail(REBOP_ERR_LIMIT, b->tables_error);
+  return REBOP_OK;
+}
+
 static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_first, uint32_t step_last,
                   int* d_out, uint32_t n_save, const uint32_t* save_idx) {
   const uint32_t S = b->net.n_species;
   SsaRunParams p;
-  std::memset(&p, 0, sizeof p);
-  p.x = b->d_x;
-  p.t = b->d_t;
-  p.rng = b->d_rng;
-  p.seeds = b->d_seeds;
-  p.seed_base = b->seed_base;
+  fill_params(b, &p);
   p.out = d_out;
-  p.events = b->d_counters;
-  p.status = reinterpret_cast<rb_u32*>(b->d_counters + 1);
   p.tmax = tmax;
-  p.n_traj = (rb_u32)b->n;
-  p.ldn = (rb_u32)b->ldn;
   p.nb_steps = nb_steps;
   p.step_first = step_first;
   p.step_last = step_last;
   p.n_save = d_out ? n_save : 0;
-  p.seed_mode = b->seed_mode;
-  p.max_iters = b->max_iters;
-  p.bias_hi = 0x43300000u;
-  p.bias = 0x1.0p52 + 0x1.0p31;
-  p.one_m_eps = 1.0 - 0x1.0p-53;
-  for (int l = 0; l < 4; ++l) p.byte_sel[l] = 1 << (8 * l);
   const unsigned n_points = step_last - step_first + 1;
 
   RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
@@ -517,46 +567,19 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     if (!std::strcmp(env, "dynamic")) schedule = 2;
   }
   const bool want_dynamic = schedule == 2 || (schedule == 0 && rb_auto_dynamic(b, tmax, p.n_save, n_points));
-  p.work_next = reinterpret_cast<rb_u32*>(b->d_counters + 3);
 
-  // --- pick the kernel: build-time specialised, else NVRTC-specialised, else table-driven ---
   RbJitKernel jit;
   bool use_jit = false;
   int jit_kind = REBOP_KERNEL_NVRTC;
-  if (b->kernel_pref == REBOP_KERNEL_AUTO || b->kernel_pref == REBOP_KERNEL_PREBUILT) {
-    int st = rb_prebuilt_get(b->net, &jit);
-    if (st == REBOP_OK) {
-      use_jit = true;
-      jit_kind = REBOP_KERNEL_PREBUILT;
-    } else if (b->kernel_pref == REBOP_KERNEL_PREBUILT) {
-      return st;
-    }
-  }
-  if (!use_jit && (b->kernel_pref == REBOP_KERNEL_AUTO || b->kernel_pref == REBOP_KERNEL_NVRTC)) {
-    int st = rb_jit_get(b->net, b->device, &jit);
-    if (st == REBOP_OK) {
-      use_jit = true;
-    } else if (b->kernel_pref == REBOP_KERNEL_NVRTC) {
-      return st;
-    }
-  }
-
-  // large specialised kernels assume non-decreasing cumulative rates: k >= 0 and counts >= 0
-  if (use_jit && jit.large) {
-    bool ok = b->x_nonneg;
-    for (const RbReaction& rx : b->net.rx) ok = ok && !(rx.k < 0.0);
-    if (!ok) {
-      if (b->kernel_pref != REBOP_KERNEL_AUTO)
-        return rb_fail(REBOP_ERR_LIMIT, "the specialised kernel for large networks needs rate constants >= 0 and counts >= 0");
-      use_jit = false;
-    }
+  {
+    int st = pick_kernel(b, false, &jit, &use_jit, &jit_kind);
+    if (st) return st;
   }
 
   RB_CUDA(cudaEventRecord(b->ev0, b->stream));
   if (use_jit) {
     // saved species: the specialised kernels take a bit mask and emit rows in ascending species order
     for (uint32_t j = 0; j < p.n_save && save_idx[j] < 128; ++j) p.save_mask[save_idx[j] >> 6] |= 1ull << (save_idx[j] & 63u);
-    for (size_t r = 0; r < b->net.rx.size() && r < RB_MAX_K; ++r) p.k[r] = b->net.rx[r].k;
     const unsigned block = jit.block;
     unsigned ctas = std::max(1u, 2048u / block / 2u);
     if (jit.large) {
@@ -582,7 +605,6 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     if (st) return st;
     b->kernel_used = jit_kind;
   } else {
-    if (!b->tables_ok) return rb_fail(REBOP_ERR_LIMIT, b->tables_error);
     if (p.n_save > RB_TAB_MAX_SAVE) return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: more than 1024 saved species");
     for (uint32_t j = 0; j < p.n_save; ++j) b->tables.save_idx[j] = (unsigned short)save_idx[j];
     {
@@ -663,6 +685,148 @@ extern "C" int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_ste
   int st = launch(b, tmax, nb_steps, 0, nb_steps, n_save ? b->d_out : nullptr, n_save, save_idx);
   if (st) return st;
   if (host_out) return rebop_batch_samples_host_i32(b, host_out);
+  return REBOP_OK;
+}
+
+// The nb_steps = 0 path of the binding (src/pyo3_gillespie.rs:209-223) for every trajectory: counting pass,
+// host prefix sum, writing pass (see rb_ssa_events).
+extern "C" int rebop_batch_run_events(rebop_batch* b, double tmax, const uint32_t* save_idx, uint32_t n_save) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  const uint32_t S = b->net.n_species;
+  std::vector<uint32_t> all;
+  if (!save_idx) {
+    all.resize(S);
+    for (uint32_t s = 0; s < S; ++s) all[s] = s;
+    save_idx = all.data();
+    n_save = S;
+  }
+  for (uint32_t j = 0; j < n_save; ++j) {
+    if (save_idx[j] >= S) return rb_fail(REBOP_ERR_OUT_OF_RANGE, "save_idx refers to a species index out of range");
+    if (j > 0 && save_idx[j] <= save_idx[j - 1]) return rb_fail(REBOP_ERR_INVALID, "save_idx must be strictly increasing");
+  }
+  RbJitKernel jit;
+  bool use_jit = false;
+  int jit_kind = REBOP_KERNEL_NVRTC;
+  int st = pick_kernel(b, true, &jit, &use_jit, &jit_kind);
+  if (st) return st;
+
+  SsaRunParams p;
+  fill_params(b, &p);
+  p.tmax = tmax;
+  p.n_save = n_save;
+  unsigned block = RB_TABLE_BLOCK;
+  size_t smem = 0;
+  if (use_jit) {
+    for (uint32_t j = 0; j < n_save && save_idx[j] < 128; ++j) p.save_mask[save_idx[j] >> 6] |= 1ull << (save_idx[j] & 63u);
+    block = jit.block;
+    smem = RB_SSA_SMEM_BYTES(jit.net_words, block, 0, 0);
+  } else {
+    if (n_save > RB_TAB_MAX_SAVE) return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: more than 1024 saved species");
+    for (uint32_t j = 0; j < n_save; ++j) b->tables.save_idx[j] = (unsigned short)save_idx[j];
+    smem = RB_SSA_SMEM_BYTES(S * block, block, 0, 0);
+    if (smem + RB_STATIC_SMEM_BYTES > (size_t)b->max_smem_optin)
+      return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: species state does not fit in shared memory");
+  }
+  if (!use_jit || jit.large) {
+    st = upload_gtab(b, save_idx, n_save);
+    if (st) return st;
+    p.gtab = b->d_gtab;
+  }
+  const unsigned grid = (unsigned)((b->n + block - 1) / block);
+  if (!b->d_ev_counts) RB_CUDA(cudaMalloc(&b->d_ev_counts, b->ldn * sizeof(rb_u32)));
+  if (!b->d_ev_offsets) RB_CUDA(cudaMalloc(&b->d_ev_offsets, b->ldn * sizeof(rb_u64)));
+  auto run_pass = [&](bool write) -> int {
+    RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
+    if (use_jit) {
+      int rc = rb_jit_launch_entry(write ? jit.kernel_evw : jit.kernel_evc, block, p, grid, smem, b->stream);
+      if (rc) return rc;
+    } else {
+      RB_CUDA(rb_table_launch_events(&b->tables, write, p, grid, smem, b->stream));
+    }
+    ++g_kernel_launches;
+    return REBOP_OK;
+  };
+
+  // pass 1: rows per trajectory
+  p.ev_counts = b->d_ev_counts;
+  RB_CUDA(cudaEventRecord(b->ev0, b->stream));
+  st = run_pass(false);
+  if (st) return st;
+  std::vector<rb_u32> counts(b->n);
+  rb_u64 counters[4] = {0, 0, 0, 0};
+  RB_CUDA(cudaMemcpyAsync(counts.data(), b->d_ev_counts, b->n * sizeof(rb_u32), cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaMemcpyAsync(counters, b->d_counters, sizeof counters, cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  if (counters[1] & RB_STATUS_ITER_CAP)
+    return rb_fail(REBOP_ERR_ITER_CAP, "a trajectory hit the per-launch iteration cap before reaching tmax (nothing was changed)");
+  b->ev_offsets.assign(b->n + 1, 0);
+  for (size_t i = 0; i < b->n; ++i) b->ev_offsets[i + 1] = b->ev_offsets[i] + counts[i];
+  const uint64_t total = b->ev_offsets[b->n];
+  if (total >= 0xffffffffull) return rb_fail(REBOP_ERR_LIMIT, "event log of more than 2^32 rows: split the ensemble");
+  size_t free_b = 0, total_b = 0;
+  RB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t need_out = std::max<size_t>(1, (size_t)total * n_save);
+  const size_t extra = (need_out > b->out_capacity ? need_out * sizeof(int) : 0) +
+                       (total > b->ev_times_capacity ? (size_t)total * sizeof(double) : 0);
+  if (extra > free_b + b->out_capacity * sizeof(int) + b->ev_times_capacity * sizeof(double))
+    return rb_fail(REBOP_ERR_LIMIT, "event log does not fit in device memory: split the ensemble or save fewer species");
+  if (need_out > b->out_capacity) {
+    if (b->d_out) RB_CUDA(cudaFree(b->d_out));
+    b->d_out = nullptr;
+    b->out_capacity = 0;
+    RB_CUDA(cudaMalloc(&b->d_out, need_out * sizeof(int)));
+    b->out_capacity = need_out;
+  }
+  if (total > b->ev_times_capacity) {
+    if (b->d_ev_times) RB_CUDA(cudaFree(b->d_ev_times));
+    b->d_ev_times = nullptr;
+    b->ev_times_capacity = 0;
+    RB_CUDA(cudaMalloc(&b->d_ev_times, std::max<size_t>(1, total) * sizeof(double)));
+    b->ev_times_capacity = total;
+  }
+  RB_CUDA(cudaMemcpyAsync(b->d_ev_offsets, b->ev_offsets.data(), b->n * sizeof(rb_u64), cudaMemcpyHostToDevice, b->stream));
+
+  // pass 2: the same trajectories again, rows written at their offsets, final state written back
+  p.ev_offsets = b->d_ev_offsets;
+  p.ev_times = b->d_ev_times;
+  p.ev_total = total;
+  p.out = n_save ? b->d_out : nullptr;
+  st = run_pass(true);
+  if (st) return st;
+  RB_CUDA(cudaEventRecord(b->ev1, b->stream));
+  RB_CUDA(cudaMemcpyAsync(counters, b->d_counters, sizeof counters, cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  RB_CUDA(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
+  b->kernel_used = use_jit ? jit_kind : REBOP_KERNEL_TABLE;
+  b->dynamic_last = false;
+  b->seed_mode = 0;
+  b->events_last = counters[0];
+  b->events_total += counters[0];
+  b->lane_slots_last = 0;
+  b->out_rows = 0;  // the grid accessors do not apply to an event log
+  b->ev_n_save = n_save;
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_events_log_size(const rebop_batch* b, uint64_t* total_rows, uint32_t* n_save) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  if (b->ev_offsets.empty()) return rb_fail(REBOP_ERR_INVALID, "no event log: call rebop_batch_run_events first");
+  if (total_rows) *total_rows = b->ev_offsets.back();
+  if (n_save) *n_save = b->ev_n_save;
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_events_log_host(rebop_batch* b, uint64_t* offsets, double* times, int32_t* samples) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  if (b->ev_offsets.empty()) return rb_fail(REBOP_ERR_INVALID, "no event log: call rebop_batch_run_events first");
+  RB_CUDA(cudaSetDevice(b->device));
+  const uint64_t total = b->ev_offsets.back();
+  if (offsets) std::memcpy(offsets, b->ev_offsets.data(), b->ev_offsets.size() * sizeof(uint64_t));
+  if (times && total) RB_CUDA(cudaMemcpyAsync(times, b->d_ev_times, total * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (samples && total && b->ev_n_save)
+    RB_CUDA(cudaMemcpyAsync(samples, b->d_out, (size_t)total * b->ev_n_save * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  RB_CUDA(cudaStreamSynchronize(b->stream));
   return REBOP_OK;
 }
 

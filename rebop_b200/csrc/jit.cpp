@@ -118,6 +118,8 @@ int rb_prebuilt_get(const rebop_network& net, RbJitKernel* out) {
   if (!e) return rb_fail(REBOP_ERR_INVALID, "no build-time kernel was generated for this network (see rebop_b200/systems)");
   out->kernel = const_cast<void*>(e->kernel);
   out->kernel_dyn = const_cast<void*>(e->kernel_dyn);
+  out->kernel_evc = const_cast<void*>(e->kernel_evc);
+  out->kernel_evw = const_cast<void*>(e->kernel_evw);
   out->block = e->block;
   out->net_words = e->net_words;
   out->static_smem = e->static_smem;
@@ -211,6 +213,46 @@ int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out) {
   e.k.large = info.large;
   g_cache[key] = e;
   *out = e.k;
+  return REBOP_OK;
+}
+
+int rb_jit_get_events(const rebop_network& net, int device, RbJitKernel* out) {
+  std::string why;
+  if (!rb_codegen_supported(net, &why)) return rb_fail(REBOP_ERR_LIMIT, "network cannot be specialised: " + why);
+  RbCodegenInfo info;
+  const std::string src = rb_codegen_source(net, "rb_ssa_jit", &info, RB_VARIANT_EVENTS);
+  std::lock_guard<std::mutex> lock(g_mutex);
+  auto key = std::make_pair(device, src);
+  auto it = g_cache.find(key);
+  if (it == g_cache.end()) {
+    std::vector<char> cubin;
+    int st = compile_to_cubin(src, &cubin);
+    if (st) return st;
+    CacheEntry e;
+    cudaError_t err = cudaLibraryLoadData(&e.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(err));
+    cudaKernel_t evc = nullptr, evw = nullptr;
+    err = cudaLibraryGetKernel(&evc, e.lib, "rb_ssa_jit_evc");
+    if (err == cudaSuccess) err = cudaLibraryGetKernel(&evw, e.lib, "rb_ssa_jit_evw");
+    if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(err));
+    e.k.kernel_evc = evc;
+    e.k.kernel_evw = evw;
+    e.k.block = info.block;
+    e.k.net_words = info.net_words;
+    e.k.static_smem = info.static_smem;
+    e.k.large = info.large;
+    it = g_cache.emplace(key, e).first;
+  }
+  *out = it->second.k;
+  return REBOP_OK;
+}
+
+int rb_jit_launch_entry(void* kernel, unsigned block, const SsaRunParams& p, unsigned grid, size_t smem_bytes, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+  void* args[] = {const_cast<SsaRunParams*>(&p)};
+  err = cudaLaunchKernel(kernel, dim3(grid), dim3(block), args, smem_bytes, stream);
+  if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLaunchKernel: ") + cudaGetErrorString(err));
   return REBOP_OK;
 }
 

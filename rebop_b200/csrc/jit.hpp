@@ -12,6 +12,8 @@
 struct RbJitKernel {
   void* kernel = nullptr;      // cudaKernel_t / __global__ function: static schedule
   void* kernel_dyn = nullptr;  // dynamic schedule
+  void* kernel_evc = nullptr;  // event-log mode: counting pass (filled by rb_jit_get_events / rb_prebuilt_get)
+  void* kernel_evw = nullptr;  // event-log mode: writing pass
   unsigned block = 128;
   unsigned net_words = 0;
   unsigned static_smem = 0;  // bytes of static shared memory beyond the ensemble loop's own
@@ -22,6 +24,10 @@ struct RbJitKernel {
 // REBOP_ERR_LIMIT when the network is too large to specialise, REBOP_ERR_NVRTC when NVRTC is
 // missing or the compilation fails (the message carries the log).
 int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out);
+// Same for the event-log kernels (a separate NVRTC program, compiled on first use).
+int rb_jit_get_events(const rebop_network& net, int device, RbJitKernel* out);
+// Launch of an arbitrary entry point of a specialised kernel.
+int rb_jit_launch_entry(void* kernel, unsigned block, const SsaRunParams& p, unsigned grid, size_t smem_bytes, cudaStream_t stream);
 // The kernel rebop_sysgen + nvcc compiled for this network at build time, if any (REBOP_ERR_INVALID if none).
 int rb_prebuilt_get(const rebop_network& net, RbJitKernel* out);
 // Source (and optionally the sm_100a cubin) of the specialised kernel; needs no GPU.

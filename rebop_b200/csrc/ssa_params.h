@@ -52,6 +52,11 @@ struct SsaRunParams {
   double one_m_eps;      // 1 - 2^-53
   int byte_sel[4];       // dp4a selectors 1, 1<<8, 1<<16, 1<<24
   rb_u64 save_mask[2];   // specialised kernels: bit s set => species s is sampled
+  // event-log mode (nb_steps = 0, src/pyo3_gillespie.rs:209-223): one row per applied reaction
+  rb_u32* ev_counts;         // [n_traj] rows of each trajectory (written by the counting pass)
+  const rb_u64* ev_offsets;  // [n_traj] first row of each trajectory (read by the writing pass)
+  double* ev_times;          // [ev_total] time of every row
+  rb_u64 ev_total;           // rows of the whole ensemble = stride of the sample rows in `out`
   const rb_u32* gtab;    // table-driven and large specialised kernels: per-reaction records (+ saved-species list)
   double k[RB_MAX_K];    // specialised kernels: rate constants (kernel parameters may be up to 32 KB on sm_70+)
 };

@@ -178,6 +178,29 @@ __global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel_dyn(const 
   rb_ssa_loop<RbTableNet, true>(net, p, rb_smem);
 }
 
+__global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel_evc(const __grid_constant__ SsaRunParams p) {
+  extern __shared__ __align__(16) int rb_smem[];
+  RbTableNet net;
+  rb_ssa_events<RbTableNet, false>(net, p, rb_smem);
+}
+__global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel_evw(const __grid_constant__ SsaRunParams p) {
+  extern __shared__ __align__(16) int rb_smem[];
+  RbTableNet net;
+  rb_ssa_events<RbTableNet, true>(net, p, rb_smem);
+}
+
+// Event-log mode: counting (write = false) or writing pass.
+cudaError_t rb_table_launch_events(const RbTables* host_tables, bool write, const SsaRunParams& p, unsigned grid,
+                                   size_t smem_bytes, cudaStream_t stream) {
+  auto kernel = write ? rb_ssa_table_kernel_evw : rb_ssa_table_kernel_evc;
+  cudaError_t err = cudaMemcpyToSymbolAsync(c_tab, host_tables, sizeof(RbTables), 0, cudaMemcpyHostToDevice, stream);
+  if (err != cudaSuccess) return err;
+  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (err != cudaSuccess) return err;
+  kernel<<<grid, RB_TABLE_BLOCK, smem_bytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t rb_table_occupancy(bool dynamic, size_t smem_bytes, int* ctas_per_sm) {
   auto kernel = dynamic ? rb_ssa_table_kernel_dyn : rb_ssa_table_kernel;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);

@@ -37,6 +37,8 @@ struct RbPrebuilt {
   const char* key;      // rb_codegen_source(net, "rb_ssa_jit") of the network it was generated from
   const void* kernel;   // __global__ function, static schedule
   const void* kernel_dyn;  // dynamic schedule
+  const void* kernel_evc;  // event-log mode: counting pass
+  const void* kernel_evw;  // event-log mode: writing pass
   unsigned block, static_smem, net_words;
   const char* name;     // system name
 };

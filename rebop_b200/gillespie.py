@@ -153,6 +153,30 @@ class Gillespie:
                 net.add_reaction_expr(program, diff)
         return net
 
+    def _run_events(self, net, n, batched, x0, seeds, tmax, names, save_names, device, kernel, dtype, reduce):
+        """nb_steps = 0 (src/pyo3_gillespie.rs:209-223): every reaction is returned, ending with the first that
+        happens at or after tmax.  One Dataset per trajectory: their lengths differ."""
+        if reduce:
+            raise ValueError("reduce=True needs a time grid (nb_steps > 0): event times differ between trajectories")
+        if not names:
+            empty = make_dataset({}, np.array([0.0, float("inf")]), batched=False)
+            return [empty] * n if batched else empty
+        uniq = sorted({self._species[v] for v in save_names})
+        row = {idx: j for j, idx in enumerate(uniq)}
+        b = _ffi.Batch(net, n, x0, seeds=seeds, device=device, kernel=kernel)
+        try:
+            offsets, times, samples = b.run_events(tmax, uniq)
+            self.last_events, self.last_kernel_ms = b.events()[1], b.last_kernel_ms
+        finally:
+            b.close()
+        samples = samples.astype(np.dtype(dtype), copy=False)
+        out = []
+        for i in range(n):
+            lo, hi = int(offsets[i]), int(offsets[i + 1])
+            out.append(make_dataset({v: samples[row[self._species[v]], lo:hi] for v in save_names}, times[lo:hi],
+                                    batched=False))
+        return out if batched else out[0]
+
     # -- simulation -----------------------------------------------------------
     def run(  # noqa: PLR0913
         self,
@@ -190,6 +214,9 @@ class Gillespie:
             (variables ``<name>_mean`` and ``<name>_var``, dim ``time``) instead of the
             trajectories; the samples never leave the GPUs.
 
+        nb_steps = 0 returns every reaction (one row per event, the last at or after `tmax`); with
+        `n_trajectories` the result is then a list of Datasets, one per trajectory (their lengths differ).
+
         Returns an `xarray.Dataset` when xarray is importable, otherwise a small stand-in with
         the same access patterns (`ds.S`, `ds["S"]`, `ds.time`).
         """
@@ -222,12 +249,11 @@ class Gillespie:
         nb_steps = int(nb_steps)
         if nb_steps < 0:
             raise OverflowError("can't convert negative int to unsigned")
-        if nb_steps == 0:
-            raise NotImplementedError(
-                "nb_steps=0 (one row per reaction, src/pyo3_gillespie.rs:209-223) has a data-dependent "
-                "output length and is not on the GPU path yet")
         net = self._lower(params, _ffi.ARITH_API)
         tmax = float(tmax)
+        if nb_steps == 0:
+            return self._run_events(net, n, n_trajectories is not None, x0, seeds, tmax, names, save_names, device,
+                                    _KERNELS[kernel], dtype, reduce)
         times = np.array([tmax * float(i) / float(nb_steps) for i in range(nb_steps + 1)], dtype=np.float64)
 
         values = {}

@@ -247,6 +247,52 @@ def test_sharding_over_devices_does_not_change_results(gpu, ffi):
 
 
 @pytest.mark.gpu
-def test_nb_steps_zero_is_refused_loudly(gpu):
-    with pytest.raises(NotImplementedError):
-        sir_model().run({"S": 999, "I": 1}, tmax=250, nb_steps=0, rng=0)
+@pytest.mark.parametrize("seed", range(10))
+def test_all_reactions(gpu, seed):
+    """tests/test_rebop.py:39-52 (nb_steps = 0)."""
+    tmax = 250
+    ds = sir_model().run({"S": 999, "I": 1}, tmax=tmax, nb_steps=0, rng=seed)
+    t = np.asarray(ds.time)
+    assert t[0] == 0
+    assert t[-1] > tmax
+    assert np.all(np.diff(t) > 0)
+    keep = slice(None, -1) if np.isinf(t[-1]) else slice(None)
+    assert set(np.diff(np.asarray(ds.S)[keep])) <= {-1, 0}
+    assert set(np.diff(np.asarray(ds.I)[keep])) <= {-1, 1}
+    assert set(np.diff(np.asarray(ds.R)[keep])) <= {0, 1}
+
+
+@pytest.mark.gpu
+def test_var_names_all_reactions(gpu):
+    """tests/test_rebop.py:68-89 (nb_steps = 0 case)."""
+    sir = sir_model()
+    init = {"S": 999, "I": 1}
+    ds_all = sir.run(init, tmax=250, nb_steps=0, rng=0, var_names=None)
+    ds_subset = sir.run(init, tmax=250, nb_steps=0, rng=0, var_names=["S", "I"])
+    assert "S" in ds_subset and "I" in ds_subset and "R" not in ds_subset
+    npt.assert_array_equal(np.asarray(ds_all.time), np.asarray(ds_subset.time))
+    for name in ("S", "I"):
+        npt.assert_array_equal(np.asarray(ds_all[name]), np.asarray(ds_subset[name]))
+
+
+@pytest.mark.gpu
+def test_all_reactions_batch_equals_single_runs_and_oracle(gpu, oracle):
+    """Event logs of a batch: trajectory i equals the i-th of N successive single runs, and the oracle's log."""
+    sir = sir_model()
+    init = {"S": 999, "I": 1}
+    n = 40
+    many = sir.run(init, tmax=100, nb_steps=0, rng=3, n_trajectories=n)
+    assert isinstance(many, list) and len(many) == n
+    gen = np.random.default_rng(3)
+    singles = [sir.run(init, tmax=100, nb_steps=0, rng=gen) for _ in range(n)]
+    from rebop_b200 import models
+    from tests.helpers import numpy_seeds, oracle_network
+    onet = oracle_network(oracle, models.sir())
+    seeds = numpy_seeds(n, rng=3)
+    for i in range(n):
+        npt.assert_array_equal(np.asarray(many[i].time), np.asarray(singles[i].time))
+        ot, ox = onet.run_events(models.sir()["x0"], int(seeds[i]), 100.0)
+        npt.assert_array_equal(np.asarray(many[i].time), ot)
+        for j, name in enumerate("SIR"):
+            npt.assert_array_equal(np.asarray(many[i][name]), np.asarray(singles[i][name]))
+            npt.assert_array_equal(np.asarray(many[i][name]), ox[:, j])

@@ -279,3 +279,56 @@ def test_dynamic_schedule_resumes_exactly(gpu, ffi, oracle):
     assert finals[1][2] == finals[2][2]
     ref, _, tot = oracle_network(oracle, model, 1).run_batch(model["x0"], seeds[:2000], 0.06, 3, threads=8)
     np.testing.assert_array_equal(finals[2][0][:2000].T, ref[-1])
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc", "prebuilt"])
+@pytest.mark.parametrize("name,tmax,arith", [("sir", 60.0, 1), ("dimers", 0.02, 1), ("vilar", 0.5, 1), ("mm_lma", 5.0, 0),
+                                              ("ring", 0.3, 0)])
+def test_event_log_bit_exact(gpu, ffi, oracle, kernel, name, tmax, arith):
+    """nb_steps = 0 (src/pyo3_gillespie.rs:209-223): every row -- time and counts -- of every trajectory equals
+    the oracle's log; the batch can be advanced further afterwards (the final state was written back)."""
+    model = models.MODELS[name]()
+    net = models.build_network(model, arith)
+    if kernel == "prebuilt" and not net.has_prebuilt:
+        pytest.skip("no build-time kernel for this network")
+    n = 70
+    seeds = numpy_seeds(n, rng=23)
+    kid = {"table": 1, "nvrtc": 2, "prebuilt": 3}[kernel]
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds, kernel=kid)
+    offsets, times, samples = b.run_events(tmax)
+    assert b.kernel_used == kid
+    onet = oracle_network(oracle, model, arith)
+    total_events = 0
+    for i in range(n):
+        ot, ox = onet.run_events(model["x0"], int(seeds[i]), tmax)
+        lo, hi = int(offsets[i]), int(offsets[i + 1])
+        np.testing.assert_array_equal(times[lo:hi], ot)
+        np.testing.assert_array_equal(samples[:, lo:hi].T, ox)
+        total_events += len(ot) - 1 - int(np.isinf(ot[-1]))
+    assert b.events()[1] == total_events
+    # state written back: species and times are those of the last row
+    last = offsets[1:].astype(np.int64) - 1
+    np.testing.assert_array_equal(b.species().T, samples[:, last])
+    np.testing.assert_array_equal(b.times(), times[last])
+    # a subset of the species
+    b2 = ffi.Batch(net, n, model["x0"], seeds=seeds, kernel=kid)
+    o2, t2, s2 = b2.run_events(tmax, save_idx=[0, len(model["species"]) - 1])
+    np.testing.assert_array_equal(t2, times)
+    np.testing.assert_array_equal(s2, samples[[0, len(model["species"]) - 1]])
+    b.close()
+    b2.close()
+
+
+def test_event_log_absorbing_and_empty(gpu, ffi):
+    """An absorbing state ends the log with t = +inf (src/gillespie.rs:281-284); a trajectory already at tmax
+    has the single initial row."""
+    net = models.build_network(models.sir())
+    b = ffi.Batch(net, 3, [10, 0, 0], seeds=np.arange(3, dtype=np.uint64))  # no infected: nothing can happen
+    offsets, times, samples = b.run_events(50.0)
+    assert offsets.tolist() == [0, 2, 4, 6]
+    assert np.all(times[0::2] == 0.0) and np.all(np.isinf(times[1::2]))
+    np.testing.assert_array_equal(samples[:, 0], [10, 0, 0])
+    b.set_time(60.0)
+    offsets, times, samples = b.run_events(50.0)
+    assert offsets.tolist() == [0, 1, 2, 3] and np.all(times == 60.0)
+    b.close()
