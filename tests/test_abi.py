@@ -220,3 +220,33 @@ def test_synthetic_network_is_reproducible_and_conserves_mass():
         assert np.dot(mass, diff) == 0 and k > 0
         assert 1 <= sum(e for _, e in terms) <= 2
     assert any(e == 2 for _, terms, _ in a["reactions"] for _, e in terms)
+
+
+def _build_c_demo(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "c_abi_demo")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "c_abi_demo.c"), "-L", os.path.join(root, "rebop_b200"),
+                           "-lrebop_b200", "-Wl,-rpath," + os.path.join(root, "rebop_b200"), "-o", exe])
+    return exe
+
+
+def test_c99_program_links_against_the_abi(tmp_path, ffi):
+    """The header is plain C99 and the library links from C: host-side entries run, compute fails loudly without a GPU."""
+    import subprocess
+    exe = _build_c_demo(tmp_path)
+    if ffi.device_count() > 0:
+        pytest.skip("covered by the gpu variant")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "specialised kernel source" in res.stdout and "no device: rebop_batch_create -> 5" in res.stdout
+
+
+@pytest.mark.gpu
+def test_c99_program_reproduces_the_golden_vector(tmp_path, ffi):
+    import subprocess
+    exe = _build_c_demo(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "S,I,R at t=250 = 0,227,773 after 1772 events" in res.stdout
