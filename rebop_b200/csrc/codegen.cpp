@@ -187,6 +187,7 @@ static std::string large_source(const rebop_network& net, const std::string& ker
   if (R == 0) o << "    return false;\n";
   else o << "    return rb_large_apply<" << R << ", BLOCK>(pick, xs, p.gtab);\n";
   o << "  }\n";
+  o << "  static __device__ __forceinline__ int none() { return " << R << "; }\n";
   o << "  __device__ __forceinline__ void record(const SsaRunParams& p, int* dst, rb_u32 stride) const {\n";
   o << "    const rb_u32* save = p.gtab + " << R * 8 << ";\n";
   o << "    for (rb_u32 j = 0; j < p.n_save; ++j) dst[(size_t)j * stride] = __double2int_rn(xs[__ldg(save + j) * BLOCK]);\n";
@@ -230,19 +231,19 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   if (info) {
     info->block = block;
     info->net_words = 0;  // the stoichiometry table is static shared memory of the generated kernel
-    info->static_smem = (unsigned)(4 * (R * dwp > 0 ? R * dwp : 4));
+    info->static_smem = (unsigned)(4 * (R + 1) * dwp);
     info->uses_param_k = true;
   }
 
   std::ostringstream o;
   o << "// generated by rebop_b200 codegen: " << S << " species, " << R << " reactions, "
     << (macro ? "define_system! arithmetic" : "function-API arithmetic") << "\n";
-  o << "#define RB_NET_STATIC_WORDS " << (R * dwp > 0 ? R * dwp : 4) << "\n";
+  o << "#define RB_NET_STATIC_WORDS " << ((R + 1) * dwp) << "\n";  // + one all-zero row: \"no reaction\"
   o << "#define RB_TICK " << tick << "u\n";
   o << "#include \"ssa_kernel.cuh\"\n\n";
 
   // packed stoichiometry table
-  o << "__constant__ int rb_delta_c[" << (R * dwp > 0 ? R * dwp : 1) << "] = {";
+  o << "__constant__ int rb_delta_c[" << (R + 1) * dwp << "] = {";
   for (int r = 0; r < R; ++r) {
     for (int w = 0; w < dwp; ++w) {
       unsigned word = 0;
@@ -258,7 +259,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
       o << buf;
     }
   }
-  if (R * dwp == 0) o << "0";
+  for (int w = 0; w < dwp; ++w) o << (R || w ? ", " : "") << "0x00000000";
   o << "};\n\n";
 
   o << "struct RbGenNet {\n";
@@ -268,7 +269,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   o << "  static __device__ __forceinline__ int smem_words(const SsaRunParams&) { return 0; }\n";
   o << "  rb_u32 tab;  // shared-window address of the packed stoichiometry rows\n";
   o << "  __device__ __forceinline__ void init(const SsaRunParams&, int*, rb_u32 tid, rb_u32 sbase) {\n";
-  o << "    for (int i = (int)tid; i < " << R * dwp << "; i += BLOCK) rb_zig.net[i] = rb_delta_c[i];\n";
+  o << "    for (int i = (int)tid; i < " << (R + 1) * dwp << "; i += BLOCK) rb_zig.net[i] = rb_delta_c[i];\n";
   o << "    tab = sbase + RB_SMEM_OFF_NET;\n";
   o << "  }\n";
   o << "  __device__ __forceinline__ void load(const SsaRunParams& p, rb_u32 traj, bool valid) {\n";
@@ -363,8 +364,9 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
       o << "    i = min(i, i2);\n";
     }
     o << "    return i;\n  }\n";
+    // row R of the table is all zeros: applying it is the branch-free \"no reaction\" (macro arithmetic: nothing
+    // matched, src/gillespie_macro.rs:150-171; any arithmetic: the ensemble loop's lanes without an event)
     o << "  __device__ __forceinline__ bool apply(const SsaRunParams& p, int i) {\n";
-    if (macro) o << "    if (i == " << R << ") return false;\n";
     // fetch the packed stoichiometry row of reaction i from shared memory
     if (dwp == 1) {
       o << "    const int w0 = rb_lds_i32(tab + 4u * i);\n";
@@ -387,10 +389,11 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
       }
     }
     for (int w = 0; w < dwp; ++w) o << "    (void)w" << w << ";\n";
-    o << "    return true;\n";
+    o << "    return i != " << R << ";\n";
   }
   o << "  }\n";
 
+  o << "  static __device__ __forceinline__ int none() { return " << R << "; }\n";
   // samples: saved species in ascending index order, selected by a launch-time bit mask
   o << "  __device__ __forceinline__ void record(const SsaRunParams& p, int* dst, rb_u32 stride) const {\n";
   o << "    rb_u32 row = 0;\n";

@@ -143,6 +143,8 @@ struct RbTableNet {
     return i;  // R: nothing matches (macro arithmetic), or no reactions at all
   }
 
+  static __device__ __forceinline__ int none() { return c_tab.n_reactions; }
+
   __device__ __forceinline__ bool apply(const SsaRunParams& p, int i) {
     if (i >= c_tab.n_reactions) return false;
     const uint4* rec = reinterpret_cast<const uint4*>(p.gtab);
