@@ -145,24 +145,28 @@ def test_conservation_and_bounds(gpu, ffi, kernel):
     assert (out[-1, 0] == 1).all() and (out[-1, 2] > 1000).all() and (out[-1, 3] < 10000).all()
 
 
+@pytest.mark.parametrize("schedule", [1, 2])
 @pytest.mark.parametrize("kernel", ["table", "nvrtc"])
-def test_nan_rate_freezes(gpu, ffi, kernel):
+def test_nan_rate_freezes(gpu, ffi, kernel, schedule):
     """src/gillespie_macro.rs:224-238: a NaN rate constant => no reaction, t = tmax."""
     net = ffi.Network(1, 1)
     net.add_reaction_lma_sparse(10.0, [], [1])
     net.add_reaction_lma_sparse(float("nan"), [(0, 1)], [-1])
     b = ffi.Batch(net, 64, [0], seeds=models.seeds_sequence(64), kernel=KERNELS[kernel])
+    b.set_schedule(schedule)
     b.advance_until(100.0)
     assert (b.species() == 0).all()
     assert (b.times() == 100.0).all()
     assert b.events()[0] == 0
 
 
+@pytest.mark.parametrize("schedule", [1, 2])
 @pytest.mark.parametrize("kernel", ["table", "nvrtc"])
-def test_no_reactions(gpu, ffi, kernel):
+def test_no_reactions(gpu, ffi, kernel, schedule):
     """src/gillespie_macro.rs:239-253."""
     net = ffi.Network(3, 0)
     b = ffi.Batch(net, 40, [42, 1337, 0], seeds=models.seeds_sequence(40), kernel=KERNELS[kernel])
+    b.set_schedule(schedule)
     b.run_grid(1e20, 3)
     out = b.samples()
     assert (out[:, 0] == 42).all() and (out[:, 1] == 1337).all() and (out[:, 2] == 0).all()
@@ -237,6 +241,32 @@ def test_full_size_properties(gpu, ffi):
     sub = np.arange(0, n, 4001, dtype=np.uint64)
     t, _, _ = run_product(ffi, model, sub, 250.0, 250, KERNELS["table"])
     np.testing.assert_array_equal(t, out[:, :, ::4001])
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc", "prebuilt"])
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("name,n,tmax,nb_steps", [
+    ("sir", 2000, 250.0, 50),        # most trajectories end absorbing before tmax, crossings every few events
+    ("dimers", 500, 0.5, 3),
+    ("mm_lma", 1000, 100.0, 20),
+    ("vilar", 96, 10.0, 10),
+])
+def test_dynamic_variant_bit_exact_vs_oracle(gpu, ffi, oracle, kernel, arith, name, n, tmax, nb_steps):
+    """The dynamic variant of every kernel (draws made ahead of the propensities, stream stepped back on
+    crossings and absorbing states, all-zero row for lanes without an event) against the oracle."""
+    model = models.MODELS[name]()
+    net = models.build_network(model, arith)
+    if kernel == "prebuilt" and not net.has_prebuilt:
+        pytest.skip("no build-time kernel for this network")
+    seeds = numpy_seeds(n, rng=5)
+    ref, _, ref_tot = oracle_network(oracle, model, arith).run_batch(model["x0"], seeds, tmax, nb_steps, threads=8)
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds, kernel={"table": 1, "nvrtc": 2, "prebuilt": 3}[kernel])
+    b.set_schedule(2)
+    b.run_grid(tmax, nb_steps)
+    assert b.schedule_used == 2
+    np.testing.assert_array_equal(b.samples(), ref)
+    assert b.events()[0] == ref_tot
+    b.close()
 
 
 @pytest.mark.parametrize("kernel", ["table", "nvrtc"])
