@@ -217,7 +217,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
       if (rx.diff[s] != 0) touched[s] = true;
 
   // development knobs (REBOP_B200_CODEGEN="block=128,minctas=0,tick=16"); the defaults are the tuned values
-  unsigned block = 128, minctas = 5, tick = 16;  // 5 CTAs of 128 threads: at most 96 registers per thread
+  unsigned block = 128, minctas = 5, tick = 16, unroll = 1;  // 5 CTAs of 128 threads: at most 96 registers per thread
   if (const char* env = std::getenv("REBOP_B200_CODEGEN")) {
     const std::string e(env);
     auto get = [&](const char* key, unsigned def) {
@@ -227,6 +227,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
     block = get("block", block);
     minctas = get("minctas", minctas);
     tick = get("tick", tick);
+    unroll = get("unroll", unroll);
   }
   if (info) {
     info->block = block;
@@ -240,6 +241,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
     << (macro ? "define_system! arithmetic" : "function-API arithmetic") << "\n";
   o << "#define RB_NET_STATIC_WORDS " << ((R + 1) * dwp) << "\n";  // + one all-zero row: \"no reaction\"
   o << "#define RB_TICK " << tick << "u\n";
+  if (unroll != 1) o << "#define RB_INNER_UNROLL " << unroll << "\n";
   o << "#include \"ssa_kernel.cuh\"\n\n";
 
   // packed stoichiometry table
