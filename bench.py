@@ -282,12 +282,15 @@ def run_gpu(args, model):
         host_seeds = _ffi.PinnedBuffer((n,), np.uint64)
         x0 = np.asarray(model["x0"], dtype=np.int64)
 
+        e2e_kernel_ms = []
+
         def e2e_step(i):
             host_seeds.array[:] = np.arange(shard_base(i), shard_base(i) + n, dtype=np.uint64)
             batch.set_species(x0)
             batch.set_time(0.0)
             batch.seed(host_seeds.array)
             batch.run_grid(args.tmax, nb, host_out=host_out.array)
+            e2e_kernel_ms.append(batch.last_kernel_ms)
             return batch.events()[1]
 
         for i in range(args.warmup):
@@ -303,6 +306,7 @@ def run_gpu(args, model):
         checksum = int(host_out.array[-1].astype(np.int64).sum())
         e2e = {"value": e2e_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 8 + S * 4),
                "d2h_bytes_per_step": int((nb + 1) * S * n * 4), "ms_per_step": e2e_s / args.steps * 1e3,
+               "kernel_ms_per_step": float(np.mean(e2e_kernel_ms[-args.steps:])),
                "trajectories_per_s": n * world * args.steps / e2e_s, "last_row_checksum": checksum,
                "api": "rebop_batch_seed + rebop_batch_run_grid(host_out) with pinned host buffers"}
         host_out.close()
