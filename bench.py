@@ -278,8 +278,21 @@ def run_gpu(args, model):
     # ---- e2e: host buffers through the C ABI ---------------------------------------------
     e2e = None
     if not args.no_e2e:
-        host_out = _ffi.PinnedBuffer((nb + 1, S, n), np.int32)
         host_seeds = _ffi.PinnedBuffer((n,), np.uint64)
+        host_memory = "pinned"
+        try:
+            host_out = _ffi.PinnedBuffer((nb + 1, S, n), np.int32)
+        except _ffi.RebopError:  # the box refuses to page-lock that much per rank: pageable host memory instead
+
+            class _Pageable:
+                def __init__(self, shape):
+                    self.array = np.empty(shape, dtype=np.int32)
+
+                def close(self):
+                    self.array = None
+
+            host_out = _Pageable((nb + 1, S, n))
+            host_memory = "pageable (page-locking the result buffer failed)"
         x0 = np.asarray(model["x0"], dtype=np.int64)
 
         e2e_kernel_ms = []
@@ -308,7 +321,7 @@ def run_gpu(args, model):
                "d2h_bytes_per_step": int((nb + 1) * S * n * 4), "ms_per_step": e2e_s / args.steps * 1e3,
                "kernel_ms_per_step": float(np.mean(e2e_kernel_ms[-args.steps:])),
                "trajectories_per_s": n * world * args.steps / e2e_s, "last_row_checksum": checksum,
-               "api": "rebop_batch_seed + rebop_batch_run_grid(host_out) with pinned host buffers"}
+               "api": "rebop_batch_seed + rebop_batch_run_grid(host_out) with host buffers", "host_memory": host_memory}
         host_out.close()
         host_seeds.close()
 

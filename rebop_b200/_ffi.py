@@ -518,7 +518,8 @@ class PinnedBuffer:
     def close(self) -> None:
         if getattr(self, "_p", None):
             self.array = None
-            lib.rebop_b200_host_free(self._p)
+            if lib is not None:  # interpreter shutdown may have dropped the module globals already
+                lib.rebop_b200_host_free(self._p)
             self._p = None
 
     def __del__(self):

@@ -217,7 +217,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
       if (rx.diff[s] != 0) touched[s] = true;
 
   // development knobs (REBOP_B200_CODEGEN="block=128,minctas=0,tick=16"); the defaults are the tuned values
-  unsigned block = 128, minctas = 5, tick = 16, unroll = 1;  // 5 CTAs of 128 threads: at most 96 registers per thread
+  unsigned block = 128, minctas = 5, tick = 16, unroll = 1, conv = 0;  // 5 CTAs of 128 threads: at most 96 registers per thread
   if (const char* env = std::getenv("REBOP_B200_CODEGEN")) {
     const std::string e(env);
     auto get = [&](const char* key, unsigned def) {
@@ -228,6 +228,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
     minctas = get("minctas", minctas);
     tick = get("tick", tick);
     unroll = get("unroll", unroll);
+    conv = get("conv", conv);
   }
   if (info) {
     info->block = block;
@@ -242,6 +243,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   o << "#define RB_NET_STATIC_WORDS " << ((R + 1) * dwp) << "\n";  // + one all-zero row: \"no reaction\"
   o << "#define RB_TICK " << tick << "u\n";
   if (unroll != 1) o << "#define RB_INNER_UNROLL " << unroll << "\n";
+  if (conv == 1) o << "#define RB_STATE_INT\n";
   o << "#include \"ssa_kernel.cuh\"\n\n";
 
   // packed stoichiometry table
@@ -266,7 +268,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
 
   o << "struct RbGenNet {\n";
   o << "  static constexpr int BLOCK = " << block << ";\n";
-  o << "  double x[" << (S ? S : 1) << "];  // biased-double form, see ssa_kernel.cuh\n";
+  o << "  rb_state x[" << (S ? S : 1) << "];  // biased-double form, see ssa_kernel.cuh\n";
   o << "  double c[" << (R ? R : 1) << "];\n";
   o << "  static __device__ __forceinline__ int smem_words(const SsaRunParams&) { return 0; }\n";
   o << "  rb_u32 tab;  // shared-window address of the packed stoichiometry rows\n";
