@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <sstream>
 
 namespace {
@@ -81,7 +82,16 @@ static void emit_kernels(std::ostringstream& o, const std::string& kernel_name, 
 }
 
 static bool small_form_ok(const rebop_network& net) {
-  return net.n_species <= RB_GEN_MAX_SPECIES && net.rx.size() <= RB_GEN_MAX_REACTIONS;
+  unsigned max_s = RB_GEN_MAX_SPECIES, max_r = RB_GEN_MAX_REACTIONS;
+  if (const char* env = std::getenv("REBOP_B200_CODEGEN")) {  // development knobs: maxs=, maxr=
+    const std::string e(env);
+    size_t pos = e.find("maxs=");
+    if (pos != std::string::npos) max_s = (unsigned)std::atoi(e.c_str() + pos + 5);
+    pos = e.find("maxr=");
+    if (pos != std::string::npos) max_r = (unsigned)std::atoi(e.c_str() + pos + 5);
+  }
+  return net.n_species <= max_s && net.rx.size() <= max_r &&
+         2 * net.n_species + 2 * net.rx.size() + RB_GEN_LOOP_REGISTERS <= RB_GEN_MAX_REGISTERS;
 }
 
 // Large form: state as f64 columns in shared memory, unrolled propensity pass with checkpoints,
@@ -217,7 +227,14 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
       if (rx.diff[s] != 0) touched[s] = true;
 
   // development knobs (REBOP_B200_CODEGEN="block=128,minctas=0,tick=16"); the defaults are the tuned values
-  unsigned block = 128, minctas = 5, tick = 16, unroll = 1, conv = 0;  // 5 CTAs of 128 threads: at most 96 registers per thread
+  // Resident CTAs asked of the compiler: as many (up to 5 = 96 registers per thread, the Vilar sweet spot)
+  // as leave room for the register-resident state (2 per species), cumulative rates (2 per reaction) and
+  // ~40 registers of loop state; larger networks get fewer CTAs instead of spills.
+  unsigned block = 128, minctas = 5, tick = 16, unroll = 1, conv = 0;
+  {
+    const unsigned need = 2u * (unsigned)S + 2u * (unsigned)R + RB_GEN_LOOP_REGISTERS;
+    while (minctas > 1 && std::min(255u, 65536u / (128u * minctas) / 8u * 8u) < need) --minctas;
+  }
   if (const char* env = std::getenv("REBOP_B200_CODEGEN")) {
     const std::string e(env);
     auto get = [&](const char* key, unsigned def) {

@@ -6,8 +6,11 @@
 
 // Register-resident state and cumulative sums bound the networks that can be specialised;
 // larger ones use the table-driven kernel (shared-memory state).
-#define RB_GEN_MAX_SPECIES 32
-#define RB_GEN_MAX_REACTIONS 48
+#define RB_GEN_MAX_SPECIES 64
+#define RB_GEN_MAX_REACTIONS 96
+// ... and together they must fit a thread's 255 registers: 2 per species + 2 per reaction + loop state
+#define RB_GEN_MAX_REGISTERS 255
+#define RB_GEN_LOOP_REGISTERS 76
 // Large form (f64 state columns in shared memory): 32-thread CTAs hold up to 100 KB / (32 * 8 B) species.
 #define RB_GEN_LARGE_MAX_SPECIES 400
 

@@ -14,7 +14,11 @@ kernel = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 tmax = float(sys.argv[4]) if len(sys.argv) > 4 else None
 nb = int(sys.argv[5]) if len(sys.argv) > 5 else None
 arith = int(sys.argv[6]) if len(sys.argv) > 6 else 0
-m = models.MODELS[name]()
+mkw = {}
+if ":" in name:  # e.g. ring:n=30
+    name, kws = name.split(":", 1)
+    mkw = {k: int(v) for k, v in (kv.split("=") for kv in kws.split(","))}
+m = models.MODELS[name](**mkw)
 tmax = m["tmax"] if tmax is None else tmax
 nb = m["nb_steps"] if nb is None else nb
 net = models.build_network(m, arith)

@@ -202,7 +202,7 @@ def test_large_network_gets_the_shared_memory_form(ffi):
 
 def test_network_no_specialised_form_can_hold(ffi):
     """Three reactant terms in a network beyond the register-resident limits: only the table-driven kernel runs it."""
-    S = 40
+    S = 120
     net = ffi.Network(S)
     diff = [0] * S
     diff[0], diff[1], diff[2], diff[3] = -1, -1, -1, 1

@@ -39,6 +39,8 @@ def test_bit_exact_vs_oracle(gpu, ffi, oracle, kernel, arith, name, n, tmax, nb_
     ("flocculation", {"n": 50}, 96, 0.02, 4),        # my_benchmark.rs:683-700: 50 species, 625 reactions
     ("ring", {"n": 50}, 96, 2.0, 4),                 # my_benchmark.rs:601-614: 50 species, 50 reactions
     ("ring", {"n": 300, "a0": 200}, 40, 1.0, 2),     # 300 species: 32-thread CTAs
+    ("ring", {"n": 40}, 96, 2.0, 4),                 # 40 species + 40 reactions: still register-resident (2 CTAs/SM)
+    ("flocculation", {"n": 16}, 96, 0.02, 4),        # 16 species, 64 reactions: register-resident
 ])
 def test_large_networks_bit_exact(gpu, ffi, oracle, arith, name, kwargs, n, tmax, nb_steps):
     """Networks beyond the register-resident limits: the shared-memory specialised form (NVRTC) and the
@@ -53,7 +55,7 @@ def test_large_networks_bit_exact(gpu, ffi, oracle, arith, name, kwargs, n, tmax
         np.testing.assert_array_equal(out, ref)
         assert ev == ref_tot
     # a subset of the species, in the middle of the index range
-    save = [3, 17, len(model["species"]) - 1]
+    save = sorted({3, len(model["species"]) // 2 + 1, len(model["species"]) - 1})
     out, _, _ = run_product(ffi, model, seeds, tmax, nb_steps, KERNELS["nvrtc"], arith, save_idx=save)
     np.testing.assert_array_equal(out, ref[:, save, :])
 
