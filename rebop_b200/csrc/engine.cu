@@ -64,6 +64,8 @@ struct rebop_batch {
   rb_u32* d_gtab = nullptr;       // large specialised kernels: reaction records + saved-species list
   size_t gtab_capacity = 0;       // words
   std::vector<rb_u32> h_gtab;
+  double* d_grid_t = nullptr;      // grid times of the current run_grid launch
+  size_t grid_t_capacity = 0;
   // event-log mode (nb_steps = 0)
   rb_u32* d_ev_counts = nullptr;
   rb_u64* d_ev_offsets = nullptr;
@@ -227,7 +229,7 @@ extern "C" void rebop_batch_destroy(rebop_batch* b) {
   if (b->own_stream && b->own_stream != b->stream) cudaStreamSynchronize(b->own_stream);
   cudaFree(b->d_x); cudaFree(b->d_t); cudaFree(b->d_rng); cudaFree(b->d_seeds);
   cudaFree(b->d_out); cudaFree(b->d_counters); cudaFree(b->d_sums); cudaFree(b->d_gtab);
-  cudaFree(b->d_ev_counts); cudaFree(b->d_ev_offsets); cudaFree(b->d_ev_times);
+  cudaFree(b->d_ev_counts); cudaFree(b->d_ev_offsets); cudaFree(b->d_ev_times); cudaFree(b->d_grid_t);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->own_stream) cudaStreamDestroy(b->own_stream);
@@ -558,6 +560,25 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   const unsigned n_points = step_last - step_first + 1;
 
   RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
+
+  // grid times, exactly as the binding computes them: tmax * i as f64 / nb_steps as f64 (src/pyo3_gillespie.rs:201)
+  std::vector<double> grid_t;
+  if (nb_steps > 0) {
+    grid_t.resize(n_points);
+    for (unsigned i = 0; i < n_points; ++i) {
+      volatile double prod = tmax * (double)(step_first + i);  // volatile: one rounding per operation, no contraction
+      grid_t[i] = prod / (double)nb_steps;
+    }
+    if (n_points > b->grid_t_capacity) {
+      if (b->d_grid_t) RB_CUDA(cudaFree(b->d_grid_t));
+      b->d_grid_t = nullptr;
+      b->grid_t_capacity = 0;
+      RB_CUDA(cudaMalloc(&b->d_grid_t, n_points * sizeof(double)));
+      b->grid_t_capacity = n_points;
+    }
+    RB_CUDA(cudaMemcpyAsync(b->d_grid_t, grid_t.data(), n_points * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    p.grid_t = b->d_grid_t;
+  }
 
   // --- schedule: dynamic when asked for, or (auto) when there are more trajectories than resident lanes
   // and samples are sparse enough that uncoalesced sample stores do not matter

@@ -35,6 +35,7 @@ struct SsaRunParams {
   rb_u64* events;        // [0] += applied reactions; [2] += lane slots (32 x loop iterations of each warp)
   rb_u32* status;        // [1] |= RB_STATUS_*
   double tmax;
+  const double* grid_t;  // [step_last - step_first + 1] grid times t_i = (tmax * i) / nb_steps, or null: single target tmax
   rb_u32 n_traj, ldn;
   rb_u32 nb_steps;       // 0 => single target tmax (Gillespie::advance_until)
   rb_u32 step_first, step_last;  // grid points handled by this launch (inclusive)
