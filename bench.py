@@ -352,6 +352,8 @@ def run_gpu(args, model):
         "frac": achieved / (fp64_peak / 1e9) if achieved else None,
         "peak_source": "measured in this run (rebop_b200_measure_fp64_rate): 8 independent non-fused DADD/DMUL chains per "
                        "thread on all SMs; MEASURED_PEAKS.json has no FP64 entry",
+        "peak_sm_mhz": fp64_mhz, "peak_lanes_per_sm_clk": fp64_peak / (fp64_mhz * 1e6) / torch.cuda.get_device_properties(local).multi_processor_count
+        if fp64_mhz else None,
         "ops_per_event": F, "events_per_launch": ev_per_launch, "ms_per_launch": ms_per_launch,
         "lane_efficiency": events / lane_slots if lane_slots else None,
         "traffic": traffic,

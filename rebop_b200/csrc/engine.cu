@@ -148,6 +148,23 @@ __global__ void __launch_bounds__(256) rb_fp64_probe_kernel(double* sink, int it
   sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// SM clock probe: one warp per SM spins on a dependent integer chain; cycles (clock64) over nanoseconds
+// (globaltimer).  Run right after the FP64 probe, while the clocks are up.
+__global__ void rb_clock_probe_kernel(int iters, unsigned long long* out) {
+  unsigned long long g0, g1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+  const long long c0 = clock64();
+  unsigned v = threadIdx.x;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) v = v * 1664525u + 1013904223u;
+  const long long c1 = clock64();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+  if (threadIdx.x == 0) {
+    out[2 * blockIdx.x] = (unsigned long long)(c1 - c0);
+    out[2 * blockIdx.x + 1] = g1 - g0 + (v == 0xdeadbeefu);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------
@@ -977,8 +994,21 @@ extern "C" int rebop_b200_measure_fp64_rate(int device, double* ops_per_second, 
   RB_CUDA(cudaGetLastError());
   const double ops = (double)blocks * threads * (double)iters * 32.0;
   if (ops_per_second) *ops_per_second = ops / (best * 1e-3);
-  // one CTA's loop spans (almost) the whole kernel when every SM holds its 8 CTAs at once
-  if (sm_clock_mhz) *sm_clock_mhz = (double)clk / (best * 1e-3) / 1e6;
+  (void)clk;
+  if (sm_clock_mhz) {
+    unsigned long long* d_probe = nullptr;
+    RB_CUDA(cudaMalloc(&d_probe, (size_t)sms * 2 * sizeof(unsigned long long)));
+    rb_clock_probe_kernel<<<sms, 32>>>(1 << 20, d_probe);
+    ++g_kernel_launches;
+    std::vector<unsigned long long> h((size_t)sms * 2);
+    RB_CUDA(cudaMemcpy(h.data(), d_probe, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_probe);
+    std::vector<double> mhz;
+    for (int i = 0; i < sms; ++i)
+      if (h[2 * i + 1]) mhz.push_back((double)h[2 * i] / (double)h[2 * i + 1] * 1e3);
+    std::sort(mhz.begin(), mhz.end());
+    *sm_clock_mhz = mhz.empty() ? 0.0 : mhz[mhz.size() / 2];  // median over the SMs
+  }
   cudaFree(sink);
   cudaFree(clocks);
   cudaEventDestroy(e0);
