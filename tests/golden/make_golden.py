@@ -31,6 +31,7 @@ CASES = [
     ("mm_lma_api", "mm_lma", 0, numpy_seeds(48, rng=5).tolist(), 100.0, 100),
     ("vilar_macro_full", "vilar", 1, list(range(16)), 200.0, 200),
     ("vilar_api_full", "vilar", 0, list(range(1000, 1008)), 200.0, 200),
+    ("synthetic_api", "synthetic", 0, list(range(24)), 0.05, 10),  # BASELINE config C5: 100 species, 500 reactions
 ]
 
 for name, mname, arith, seeds, tmax, nb in CASES:
