@@ -2,6 +2,7 @@
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -250,3 +251,18 @@ def test_c99_program_reproduces_the_golden_vector(tmp_path, ffi):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "S,I,R at t=250 = 0,227,773 after 1772 events" in res.stdout
+
+
+def test_rust_sys_crate_is_current_and_complete(ffi):
+    """bindings/rust/rebop-b200-sys/src/lib.rs is generated from the header (no Rust toolchain here): it must be
+    up to date and declare every exported function; the safe wrapper may only call declared functions."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.call([sys.executable, os.path.join(root, "scripts", "gen_rust_sys.py"), "--check"]) == 0
+    sys_rs = open(os.path.join(root, "bindings", "rust", "rebop-b200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (rebop_\w+)\(", sys_rs))
+    assert declared == set(ffi.SIGNATURES)
+    wrapper = open(os.path.join(root, "bindings", "rust", "rebop-b200", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::(rebop_\w+)\(", wrapper))
+    assert used and used <= declared
+    consts = set(re.findall(r"sys::(REBOP_\w+)", wrapper))
+    assert consts <= set(re.findall(r"pub const (REBOP_\w+):", sys_rs))
