@@ -485,13 +485,13 @@ static int upload_gtab(rebop_batch* b, const uint32_t* save_idx, uint32_t n_save
   return REBOP_OK;
 }
 
-// Auto schedule.  Dynamic claiming pays when trajectories are long compared with the samples they emit
-// (no lane idles behind the slowest trajectory of its warp); the static schedule pays when samples are
-// dense (ring-staged, coalesced rows).  The number of events is not known in advance; the total
+// Auto schedule.  The dynamic variant pays when trajectories are long compared with the samples they emit
+// (no lane idles behind the slowest trajectory of its warp, and its pass draws ahead and runs straight-line:
+// faster even when the whole ensemble is resident at once); the static schedule pays when samples are
+// dense (ring-staged, coalesced rows, no stream step-back per crossing).  The number of events is not known in advance; the total
 // propensity of the first trajectory's initial state times the horizon is a (low) estimate that orders
 // the workloads correctly: SIR 0.04 events per sample, Dimers 3, Vilar 5, Michaelis-Menten 15.
 static bool rb_auto_dynamic(const rebop_batch* b, double tmax, unsigned n_save, unsigned n_points) {
-  if (b->n <= (size_t)b->sm_count * 2048u / 2u) return false;  // everything is resident at once anyway
   if (n_save == 0) return true;
   double a0 = 0.0;
   for (const RbReaction& rx : b->net.rx) {

@@ -253,9 +253,11 @@ def test_full_size_properties(gpu, ffi):
     ("mm_lma", 1000, 100.0, 20),
     ("vilar", 96, 10.0, 10),
 ])
-def test_dynamic_variant_bit_exact_vs_oracle(gpu, ffi, oracle, kernel, arith, name, n, tmax, nb_steps):
-    """The dynamic variant of every kernel (draws made ahead of the propensities, stream stepped back on
-    crossings and absorbing states, all-zero row for lanes without an event) against the oracle."""
+@pytest.mark.parametrize("schedule", [1, 2])
+def test_both_variants_bit_exact_vs_oracle(gpu, ffi, oracle, kernel, arith, name, n, tmax, nb_steps, schedule):
+    """Both variants of every kernel, forced: static (ring-staged samples, uniform from a copy of the stream)
+    and dynamic (draws made ahead of the propensities, stream stepped back on crossings and absorbing states,
+    all-zero row for lanes without an event) against the oracle."""
     model = models.MODELS[name]()
     net = models.build_network(model, arith)
     if kernel == "prebuilt" and not net.has_prebuilt:
@@ -263,9 +265,9 @@ def test_dynamic_variant_bit_exact_vs_oracle(gpu, ffi, oracle, kernel, arith, na
     seeds = numpy_seeds(n, rng=5)
     ref, _, ref_tot = oracle_network(oracle, model, arith).run_batch(model["x0"], seeds, tmax, nb_steps, threads=8)
     b = ffi.Batch(net, n, model["x0"], seeds=seeds, kernel={"table": 1, "nvrtc": 2, "prebuilt": 3}[kernel])
-    b.set_schedule(2)
+    b.set_schedule(schedule)
     b.run_grid(tmax, nb_steps)
-    assert b.schedule_used == 2
+    assert b.schedule_used == schedule
     np.testing.assert_array_equal(b.samples(), ref)
     assert b.events()[0] == ref_tot
     b.close()
