@@ -409,6 +409,9 @@ def main():
     ap.add_argument("--ref-traj-per-core", type=int, default=512, help="--impl reference: trajectories per core per step")
     args = ap.parse_args()
 
+    if not os.path.exists(os.path.join(ROOT, "rebop_b200", "librebop_b200.so")) and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "rebop_b200", "csrc"), "-j8"], stdout=sys.stderr)
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=sys.stderr)
     from rebop_b200 import models
     model = models.MODELS[args.model]()
     args.tmax = model["tmax"] if args.tmax is None else args.tmax

@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a clean checkout has no built library (it is git-ignored): build it once, loudly, before collection
+    if not os.path.exists(os.path.join(ROOT, "rebop_b200", "librebop_b200.so")):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "rebop_b200", "csrc"), "-j8"])
 
 
 @pytest.fixture(scope="session")
