@@ -4,7 +4,7 @@
 // (src/gillespie_macro.rs:49-129): species become scalars (registers), every propensity is one
 // straight-line expression, the cumulative sum and the reaction choice are fully unrolled.
 // The same generator serves the run-time path (NVRTC, jit.cpp) and the build-time path
-// (tools/rebop_sysgen -> nvcc).  It has no CUDA dependency.
+// (rebop_sysgen, sysgen_main.cpp -> nvcc).  It has no CUDA dependency.
 #include "codegen.hpp"
 
 #include "ssa_params.h"

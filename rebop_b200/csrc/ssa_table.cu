@@ -106,7 +106,7 @@ struct RbTableNet {
     return acc;
   }
 
-  // make_cumrates (src/gillespie.rs:357-364); only the total is kept, fire() re-walks the sum.
+  // make_cumrates (src/gillespie.rs:357-364); only the total is kept, select() re-walks the sum.
   __device__ __forceinline__ double propensities(const SsaRunParams& p) const {
     const int R = c_tab.n_reactions;
     const uint4* rec = reinterpret_cast<const uint4*>(p.gtab);
