@@ -128,52 +128,77 @@ def run_reference(args, model):
 # clocks sampler
 # --------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled during the timed region.
 
-    def __init__(self, device):
+    NVML is queried directly from a thread of this process (pynvml).  Polling through the nvidia-smi
+    binary was measured to perturb short workloads: attaching to the driver takes about a second and every
+    poll delays kernel launches by tens of milliseconds (a 110 ms step became 147 ms)."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, device, period=0.25):
         self.device = device
-        self.proc = None
-        self.path = None
+        self.period = period
+        self.samples = []
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.error = None
+        self.skip = 0
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.device < len(ids) and ids[self.device].isdigit():
+                return int(ids[self.device])
+        return self.device
 
     def start(self):
         try:
-            fh = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
-            self.path = fh.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.device)], stdout=fh, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001 - NVML missing or refusing: the run goes on without clock samples
+            self.error = f"NVML unavailable: {e}"
+            return
+
+        def loop():
+            while not self.stop_flag.is_set():
+                try:
+                    sm = float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                    power = pynvml.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                    try:
+                        reasons = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                    except AttributeError:
+                        reasons = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                    self.samples.append((sm, power, reasons))
+                except Exception as e:  # noqa: BLE001
+                    self.error = f"NVML query failed: {e}"
+                    return
+                self.stop_flag.wait(self.period)
+
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def mark(self):
+        """Samples taken so far (warm-up) are not part of the report."""
+        self.skip = len(self.samples)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for raw in open(self.path):
-            f = [c.strip() for c in raw.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.error or "sampler not started"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=5)
+        samples = self.samples[self.skip:] or self.samples[-1:]
+        if not samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.error or "no samples"]}
+        seen = 0
+        for _, _, r in samples:
+            seen |= r
+        return {"sm_mhz": float(np.median([s[0] for s in samples])), "sm_max_mhz": self.sm_max,
+                "power_w_max": max(s[1] for s in samples), "samples": len(samples),
+                "reasons": sorted(name for name, bit in self.REASONS.items() if seen & bit)}
 
 
 # --------------------------------------------------------------------------------------
@@ -238,12 +263,15 @@ def run_gpu(args, model):
     lane_slots = 0
 
     # ---- value: device-resident -------------------------------------------------------
+    # the clock sampler (nvidia-smi polling) starts before the warm-up so that its start-up cost -- it
+    # briefly contends for the driver -- is not inside the timed region; it keeps sampling through it
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         device_step(i)
-    sampler = ClockSampler(local)
     launches0 = _ffi.kernel_launches()
     barrier()
-    sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     events = 0
