@@ -87,6 +87,22 @@ __global__ void rb_fill_state_kernel(int* x, double* t, const int* x0, unsigned 
   if (fill_t) t[i] = t0;
 }
 
+// K5: SmallRng::seed_from_u64 for every trajectory (src/gillespie.rs:184,190): SplitMix64 fills the xoshiro256++
+// state.  A kernel of its own, so that every trajectory is seeded whatever the main launch gets to (a dynamic
+// launch stopped by the watchdog leaves unclaimed trajectories untouched).
+__global__ void rb_seed_kernel(rb_u64* rng, const rb_u64* seeds, rb_u64 seed_base, unsigned n, unsigned ldn) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rb_u64 st = seeds ? seeds[i] : seed_base + i;
+  for (int w = 0; w < 4; ++w) {
+    st += 0x9e3779b97f4a7c15ull;
+    rb_u64 z = st;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    rng[(size_t)w * ldn + i] = z ^ (z >> 31);
+  }
+}
+
 // K4: exact integer sum and sum of squares of every sample row over the trajectories.
 // rows are 128-byte aligned (ldn % 32 == 0); one CTA reduces a segment of one row.
 __global__ void __launch_bounds__(256) rb_row_sums_kernel(const int* __restrict__ samples, unsigned n,
@@ -506,19 +522,27 @@ static bool rb_auto_dynamic(const rebop_batch* b, double tmax, unsigned n_save, 
   return a0 * tmax >= (double)n_save * n_points;
 }
 
+// Pending seeding (rebop_batch_create / rebop_batch_seed) is applied on the stream before the next launch.
+static int apply_seeding(rebop_batch* b) {
+  if (b->seed_mode == 0) return REBOP_OK;
+  rb_seed_kernel<<<(unsigned)((b->n + 255) / 256), 256, 0, b->stream>>>(b->d_rng, b->seed_mode == 1 ? b->d_seeds : nullptr,
+                                                                      b->seed_base, (unsigned)b->n, (unsigned)b->ldn);
+  RB_CUDA(cudaGetLastError());
+  ++g_kernel_launches;
+  b->seed_mode = 0;  // streams are live on the device from now on
+  return REBOP_OK;
+}
+
 static void fill_params(const rebop_batch* b, SsaRunParams* p) {
   std::memset(p, 0, sizeof *p);
   p->x = b->d_x;
   p->t = b->d_t;
   p->rng = b->d_rng;
-  p->seeds = b->d_seeds;
-  p->seed_base = b->seed_base;
   p->events = b->d_counters;
   p->status = reinterpret_cast<rb_u32*>(b->d_counters + 1);
   p->work_next = reinterpret_cast<rb_u32*>(b->d_counters + 3);
   p->n_traj = (rb_u32)b->n;
   p->ldn = (rb_u32)b->ldn;
-  p->seed_mode = b->seed_mode;
   p->max_iters = b->max_iters;
   p->bias_hi = 0x43300000u;
   p->bias = 0x1.0p52 + 0x1.0p31;
@@ -566,6 +590,10 @@ static int pick_kernel(rebop_batch* b, bool events, RbJitKernel* jit, bool* use_
 static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_first, uint32_t step_last,
                   int* d_out, uint32_t n_save, const uint32_t* save_idx) {
   const uint32_t S = b->net.n_species;
+  {
+    int st = apply_seeding(b);
+    if (st) return st;
+  }
   SsaRunParams p;
   fill_params(b, &p);
   p.out = d_out;
@@ -597,8 +625,7 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     p.grid_t = b->d_grid_t;
   }
 
-  // --- schedule: dynamic when asked for, or (auto) when there are more trajectories than resident lanes
-  // and samples are sparse enough that uncoalesced sample stores do not matter
+  // --- schedule: dynamic when asked for, or (auto) when samples are sparse enough (rb_auto_dynamic)
   int schedule = b->schedule;
   if (const char* env = std::getenv("REBOP_B200_SCHEDULE")) {
     if (!std::strcmp(env, "static")) schedule = 1;
@@ -675,7 +702,6 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   RB_CUDA(cudaStreamSynchronize(b->stream));
   RB_CUDA(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
   b->dynamic_last = p.dynamic != 0;
-  b->seed_mode = 0;  // streams are live on the device from now on
   b->events_last = counters[0];
   b->lane_slots_last = counters[2];
   b->events_total += counters[0];
@@ -749,6 +775,8 @@ extern "C" int rebop_batch_run_events(rebop_batch* b, double tmax, const uint32_
   int st = pick_kernel(b, true, &jit, &use_jit, &jit_kind);
   if (st) return st;
 
+  st = apply_seeding(b);
+  if (st) return st;
   SsaRunParams p;
   fill_params(b, &p);
   p.tmax = tmax;
@@ -838,7 +866,6 @@ extern "C" int rebop_batch_run_events(rebop_batch* b, double tmax, const uint32_
   RB_CUDA(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
   b->kernel_used = use_jit ? jit_kind : REBOP_KERNEL_TABLE;
   b->dynamic_last = false;
-  b->seed_mode = 0;
   b->events_last = counters[0];
   b->events_total += counters[0];
   b->lane_slots_last = 0;

@@ -28,9 +28,7 @@ typedef unsigned int rb_u32;
 struct SsaRunParams {
   int* x;                // [S][ldn] species counts, trajectory-contiguous
   double* t;             // [ldn] current time of each trajectory
-  rb_u64* rng;           // [4][ldn] xoshiro256++ state
-  const rb_u64* seeds;   // [n_traj] or null; non-null => seed instead of loading rng
-  rb_u64 seed_base;      // used when seed_mode == 2: seed_n = seed_base + n
+  rb_u64* rng;           // [4][ldn] xoshiro256++ state (seeded by the engine's rb_seed_kernel before the first launch)
   int* out;              // [(step-step_first)][n_save][ldn] samples, or null
   rb_u64* events;        // [0] += applied reactions; [2] += lane slots (32 x loop iterations of each warp)
   rb_u32* status;        // [1] |= RB_STATUS_*
@@ -41,7 +39,6 @@ struct SsaRunParams {
   rb_u32 step_first, step_last;  // grid points handled by this launch (inclusive)
   rb_u32 n_save;         // rows per sample
   rb_u32 ring_depth;     // power of two, 1..32: grid points a warp can stage in shared memory
-  rb_u32 seed_mode;      // 0 load rng, 1 seeds[], 2 seed_base + n
   rb_u32 max_iters;      // per-trajectory loop-iteration cap for this launch (0 = 2^32-1)
   rb_u32 dynamic;        // 1: lanes claim further trajectories from *work_next when theirs is finished (ring_depth must be 0)
   rb_u32 n_launched;     // dynamic: threads of the grid = trajectories assigned statically at the start

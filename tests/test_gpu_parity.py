@@ -188,15 +188,32 @@ def test_sample_sums(gpu, ffi, kernel):
     np.testing.assert_array_equal(s2.reshape(21, 3).astype(np.int64), (out * out).sum(axis=2))
 
 
+@pytest.mark.parametrize("schedule", [1, 2])
 @pytest.mark.parametrize("kernel", ["table", "nvrtc"])
-def test_iteration_cap_is_reported(gpu, ffi, kernel):
-    model = models.sir()
+def test_iteration_cap_is_reported(gpu, ffi, oracle, kernel, schedule):
+    """The watchdog stops a launch between two passes; advance_until can then simply be called again and ends
+    where an uninterrupted run ends (state, time and streams are written back)."""
+    model = models.dimers()
     net = models.build_network(model)
-    b = ffi.Batch(net, 64, model["x0"], seeds=models.seeds_sequence(64), kernel=KERNELS[kernel])
-    b.set_max_iters(10)
-    with pytest.raises(ffi.RebopError) as e:
-        b.run_grid(250.0, 250)
-    assert e.value.status == ffi.ERR_ITER_CAP
+    n = 64
+    seeds = models.seeds_sequence(n)
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds, kernel=KERNELS[kernel])
+    b.set_schedule(schedule)
+    b.set_max_iters(64)
+    calls = 0
+    while True:
+        calls += 1
+        try:
+            b.advance_until(0.05)
+            break
+        except ffi.RebopError as e:
+            assert e.status == ffi.ERR_ITER_CAP
+            assert calls < 200
+    assert calls > 2
+    ref, _, tot = oracle_network(oracle, model).run_batch(model["x0"], seeds, 0.05, 0)
+    np.testing.assert_array_equal(b.species().T, ref[-1])
+    assert b.events()[0] == tot
+    assert (b.times() == 0.05).all()
 
 
 @pytest.mark.parametrize("kernel", ["table", "nvrtc"])
@@ -365,4 +382,29 @@ def test_event_log_absorbing_and_empty(gpu, ffi):
     b.set_time(60.0)
     offsets, times, samples = b.run_events(50.0)
     assert offsets.tolist() == [0, 1, 2, 3] and np.all(times == 60.0)
+    b.close()
+
+
+def test_watchdog_with_unclaimed_trajectories(gpu, ffi, oracle):
+    """Dynamic schedule, more trajectories than resident lanes, launches cut short by the watchdog: trajectories
+    that were never claimed in a launch must still start from their own seed in a later one."""
+    model = models.dimers()
+    net = models.build_network(model, 1)
+    n = 130_000
+    seeds = numpy_seeds(n, rng=17)
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds)
+    b.set_schedule(2)
+    b.set_max_iters(64)
+    calls = 0
+    while True:
+        calls += 1
+        try:
+            b.advance_until(0.05)
+            break
+        except ffi.RebopError as e:
+            assert e.status == ffi.ERR_ITER_CAP and calls < 400
+    assert calls > 1
+    ref, _, tot = oracle_network(oracle, model, 1).run_batch(model["x0"], seeds, 0.05, 0, threads=8)
+    np.testing.assert_array_equal(b.species().T, ref[-1])
+    assert b.events()[0] == tot
     b.close()
