@@ -30,7 +30,6 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
 import threading
 import time
 

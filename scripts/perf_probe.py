@@ -4,7 +4,7 @@ import time
 
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
+
 
 from rebop_b200 import _ffi, models
 

@@ -4,7 +4,6 @@
 Host-only behaviour (model building, printing, error messages) runs without a GPU; everything
 that simulates is marked gpu and goes through the C ABI.
 """
-import warnings
 
 import numpy as np
 import numpy.testing as npt
