@@ -180,7 +180,8 @@ int rebop_batch_advance_until(rebop_batch* b, double tmax);
  * species indices, or NULL for all species.
  * Samples stay on the device as int32 [nb_steps+1][n_save][ld] (ld >= n_traj).
  * host_out (optional): caller buffer of (nb_steps+1)*n_save*n_traj int32 that receives them
- * densely as [step][save][trajectory]. */
+ * densely as [step][save][trajectory]; a large result is then produced in a few segments of consecutive
+ * grid points, each copied to the host while the next is simulated (page-locked memory makes that overlap). */
 int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
                          uint32_t n_save, int32_t* host_out);
 /* The nb_steps = 0 path of the binding (src/pyo3_gillespie.rs:209-223) for every trajectory:

@@ -64,6 +64,7 @@ struct rebop_batch {
   rb_u32* d_gtab = nullptr;       // large specialised kernels: reaction records + saved-species list
   size_t gtab_capacity = 0;       // words
   std::vector<rb_u32> h_gtab;
+  cudaStream_t copy_stream = nullptr;  // run_grid(host_out): result rows go to the host while the next segment runs
   double* d_grid_t = nullptr;      // grid times of the current run_grid launch
   size_t grid_t_capacity = 0;
   // event-log mode (nb_steps = 0)
@@ -265,6 +266,7 @@ extern "C" void rebop_batch_destroy(rebop_batch* b) {
   cudaFree(b->d_ev_counts); cudaFree(b->d_ev_offsets); cudaFree(b->d_ev_times); cudaFree(b->d_grid_t);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   if (b->own_stream) cudaStreamDestroy(b->own_stream);
   delete b;
 }
@@ -588,7 +590,7 @@ static int pick_kernel(rebop_batch* b, bool events, RbJitKernel* jit, bool* use_
 }
 
 static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_first, uint32_t step_last,
-                  int* d_out, uint32_t n_save, const uint32_t* save_idx) {
+                  int* d_out, uint32_t n_save, const uint32_t* save_idx, unsigned grid_points_total = 0) {
   const uint32_t S = b->net.n_species;
   {
     int st = apply_seeding(b);
@@ -631,7 +633,8 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     if (!std::strcmp(env, "static")) schedule = 1;
     if (!std::strcmp(env, "dynamic")) schedule = 2;
   }
-  const bool want_dynamic = schedule == 2 || (schedule == 0 && rb_auto_dynamic(b, tmax, p.n_save, n_points));
+  const bool want_dynamic =
+      schedule == 2 || (schedule == 0 && rb_auto_dynamic(b, tmax, p.n_save, grid_points_total ? grid_points_total : n_points));
 
   RbJitKernel jit;
   bool use_jit = false;
@@ -746,10 +749,43 @@ extern "C" int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_ste
   b->out_rows = (uint32_t)rows;
   b->out_n_save = n_save;
   b->out_nb_steps = nb_steps;
-  int st = launch(b, tmax, nb_steps, 0, nb_steps, n_save ? b->d_out : nullptr, n_save, save_idx);
-  if (st) return st;
-  if (host_out) return rebop_batch_samples_host_i32(b, host_out);
-  return REBOP_OK;
+  // With a host buffer and a result worth the trouble, the grid runs as a few segments of consecutive grid
+  // points: the rows of a finished segment travel to the host while the next segment is being simulated
+  // (a launch that ends at grid point k leaves every trajectory exactly where a single launch would have it
+  // at that point, so the result does not depend on the segmentation).
+  const size_t bytes = rows * b->n * sizeof(int);
+  unsigned segments = 1;
+  if (host_out && n_save && bytes >= ((size_t)256 << 20) && nb_steps + 1 >= 8) segments = 4;
+  if (segments == 1) {
+    int st = launch(b, tmax, nb_steps, 0, nb_steps, n_save ? b->d_out : nullptr, n_save, save_idx);
+    if (st) return st;
+    if (host_out) return rebop_batch_samples_host_i32(b, host_out);
+    return REBOP_OK;
+  }
+  if (!b->copy_stream) RB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+  uint64_t events = 0, lane_slots = 0;
+  float ms = 0.f;
+  int st = REBOP_OK;
+  for (unsigned sgm = 0; sgm < segments && st == REBOP_OK; ++sgm) {
+    const uint32_t first = (uint32_t)((uint64_t)(nb_steps + 1) * sgm / segments);
+    const uint32_t last = (uint32_t)((uint64_t)(nb_steps + 1) * (sgm + 1) / segments) - 1;
+    st = launch(b, tmax, nb_steps, first, last, b->d_out + (size_t)first * n_save * b->ldn, n_save, save_idx, nb_steps + 1);
+    events += b->events_last;
+    lane_slots += b->lane_slots_last;
+    ms += b->last_ms;
+    if (st == REBOP_OK) {
+      cudaError_t err = cudaMemcpy2DAsync(host_out + (size_t)first * n_save * b->n, b->n * sizeof(int),
+                                          b->d_out + (size_t)first * n_save * b->ldn, b->ldn * sizeof(int), b->n * sizeof(int),
+                                          (size_t)(last - first + 1) * n_save, cudaMemcpyDeviceToHost, b->copy_stream);
+      if (err != cudaSuccess) st = rb_fail(REBOP_ERR_CUDA, std::string("cudaMemcpy2DAsync: ") + cudaGetErrorString(err));
+    }
+  }
+  cudaError_t err = cudaStreamSynchronize(b->copy_stream);
+  if (st == REBOP_OK && err != cudaSuccess) st = rb_fail(REBOP_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(err));
+  b->events_last = events;
+  b->lane_slots_last = lane_slots;
+  b->last_ms = ms;
+  return st;
 }
 
 // The nb_steps = 0 path of the binding (src/pyo3_gillespie.rs:209-223) for every trajectory: counting pass,

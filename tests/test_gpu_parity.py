@@ -408,3 +408,37 @@ def test_watchdog_with_unclaimed_trajectories(gpu, ffi, oracle):
     np.testing.assert_array_equal(b.species().T, ref[-1])
     assert b.events()[0] == tot
     b.close()
+
+
+def test_segmented_run_with_host_buffer(gpu, ffi, oracle):
+    """run_grid(host_out) on a large result runs the grid in segments and copies finished rows while the next
+    segment is simulated: same samples, events and final state as one launch, and as the oracle."""
+    model = models.sir()
+    n = 300_000  # 251 x 3 x n x 4 B = 904 MB > the segmentation threshold
+    seeds = models.seeds_sequence(n, first=77)
+    net = models.build_network(model)
+    a = ffi.Batch(net, n, model["x0"], seeds=seeds)
+    host = np.empty((251, 3, n), dtype=np.int32)
+    a.run_grid(250.0, 250, host_out=host)
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds)
+    b.run_grid(250.0, 250)
+    np.testing.assert_array_equal(host, b.samples())
+    np.testing.assert_array_equal(a.samples(), host)  # the device copy is whole as well
+    assert a.events() == b.events()
+    np.testing.assert_array_equal(a.species(), b.species())
+    np.testing.assert_array_equal(a.times(), b.times())
+    ref, _, _ = oracle_network(oracle, model).run_batch(model["x0"], seeds[:3000], 250.0, 250, threads=8)
+    np.testing.assert_array_equal(host[:, :, :3000], ref)
+    # event-dense network through the dynamic variant
+    model = models.dimers()
+    n = 2_000_000
+    net = models.build_network(model, 1)
+    a = ffi.Batch(net, n, model["x0"], seeds=None, seed_base=5)
+    a.set_schedule(2)
+    host = np.empty((16, 4, n), dtype=np.int32)  # 512 MB
+    a.run_grid(0.15, 15, host_out=host)
+    assert a.schedule_used == 2
+    ref, _, _ = oracle_network(oracle, model, 1).run_batch(model["x0"], models.seeds_sequence(2000, 5), 0.15, 15, threads=8)
+    np.testing.assert_array_equal(host[:, :, :2000], ref)
+    a.close()
+    b.close()
