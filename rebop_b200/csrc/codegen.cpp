@@ -232,7 +232,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   // ~40 registers of loop state; larger networks get fewer CTAs instead of spills.
   unsigned block = 128, minctas = 5, tick = 16, unroll = 1, conv = 0;
   {
-    const unsigned need = 2u * (unsigned)S + 2u * (unsigned)R + RB_GEN_LOOP_REGISTERS;
+    const unsigned need = 2u * (unsigned)S + 2u * (unsigned)R + RB_GEN_LOOP_REGISTERS_TIGHT((unsigned)S, (unsigned)R);
     while (minctas > 1 && std::min(255u, 65536u / (128u * minctas) / 8u * 8u) < need) --minctas;
   }
   if (const char* env = std::getenv("REBOP_B200_CODEGEN")) {

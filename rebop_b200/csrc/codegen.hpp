@@ -10,7 +10,11 @@
 #define RB_GEN_MAX_REACTIONS 96
 // ... and together they must fit a thread's 255 registers: 2 per species + 2 per reaction + loop state
 #define RB_GEN_MAX_REGISTERS 255
-#define RB_GEN_LOOP_REGISTERS 76
+#define RB_GEN_LOOP_REGISTERS 86
+// what the compiler needs next to state and cumulative rates when the launch bound asks it to be tight: 40
+// registers of loop state plus temporaries that grow with the width of the stoichiometry rows
+// (Vilar: 18 + 32 + 40 + 6 = 96 registers at 5 resident CTAs); used to choose the launch bound
+#define RB_GEN_LOOP_REGISTERS_TIGHT(S, R) (40u + ((S) + (R)) / 4u)
 // Large form (f64 state columns in shared memory): 32-thread CTAs hold up to 100 KB / (32 * 8 B) species.
 #define RB_GEN_LARGE_MAX_SPECIES 400
 

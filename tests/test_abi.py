@@ -266,3 +266,27 @@ def test_rust_sys_crate_is_current_and_complete(ffi):
     assert used and used <= declared
     consts = set(re.findall(r"sys::(REBOP_\w+)", wrapper))
     assert consts <= set(re.findall(r"pub const (REBOP_\w+):", sys_rs))
+
+
+@pytest.mark.parametrize("name,kwargs,arith,max_regs", [
+    ("vilar", {}, 1, 96),          # 5 CTAs of 128 threads per SM
+    ("vilar", {}, 0, 96),
+    ("dimers", {}, 1, 96),
+    ("ring", {"n": 40}, 0, 255),   # register-resident at 2 CTAs per SM
+    ("synthetic", {}, 0, 255),     # shared-memory form
+])
+def test_generated_kernels_fit_their_register_budget_without_spills(ffi, tmp_path, name, kwargs, arith, max_regs):
+    """Resource usage of the NVRTC cubins (no GPU needed): the occupancy the launch logic assumes, and no
+    local-memory spills in any of the specialised kernels."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    net = models.build_network(models.MODELS[name](**kwargs), arith)
+    cubin = tmp_path / "k.cubin"
+    cubin.write_bytes(net.jit_cubin())
+    usage = subprocess.check_output(["cuobjdump", "-res-usage", str(cubin)], text=True)
+    found = re.findall(r"Function (rb_ssa_jit\w*):\s*\n\s*REG:(\d+) STACK:(\d+)", usage)
+    assert {f[0] for f in found} == {"rb_ssa_jit", "rb_ssa_jit_dyn"}
+    for fn, regs, stack in found:
+        assert int(regs) <= max_regs, (fn, regs)
+        assert int(stack) == 0, (fn, "spills", stack)
