@@ -38,7 +38,9 @@ typedef enum {
   REBOP_ERR_CUDA = 5,          /* CUDA runtime error, or no device */
   REBOP_ERR_NVRTC = 6,         /* run-time specialisation failed; message holds the compile log */
   REBOP_ERR_LIMIT = 7,         /* network too large for the selected kernel */
-  REBOP_ERR_ITER_CAP = 8       /* a trajectory hit the per-launch iteration cap (state is kept; call again) */
+  REBOP_ERR_ITER_CAP = 8,      /* a trajectory hit the per-launch iteration cap: state, streams and samples so far are
+                                  kept; repeating the call with the same arguments continues it exactly */
+  REBOP_ERR_NCCL = 9           /* NCCL missing or failing (rebop_ensemble_stats over several devices) */
 } rebop_status;
 
 /* Arithmetic flavour: which of the reference's two engines is reproduced bit for bit. */
@@ -54,6 +56,12 @@ typedef enum {
   REBOP_KERNEL_NVRTC = 2,  /* K2: network-specialised source compiled at run time */
   REBOP_KERNEL_PREBUILT = 3 /* K2: network-specialised source compiled at build time (rebop_sysgen + nvcc) */
 } rebop_kernel_kind;
+
+/* Sample type of a batch's time-grid results (the value is the size in bytes).  The reference returns isize
+ * (src/pyo3_gillespie.rs:224-237); counts on the device are int32, so REBOP_SAMPLES_I64 only widens.  REBOP_SAMPLES_I16
+ * halves the HBM and PCIe traffic of sample-dense runs; a count outside the int16 range makes the run fail with
+ * REBOP_ERR_LIMIT instead of wrapping. */
+typedef enum { REBOP_SAMPLES_I16 = 2, REBOP_SAMPLES_I32 = 4, REBOP_SAMPLES_I64 = 8 } rebop_sample_dtype;
 
 /* Expression byte-code = post-order walk of `Expr` (src/expr.rs:9-21). */
 typedef enum {
@@ -159,13 +167,26 @@ int rebop_batch_get_kernel(const rebop_batch* b, int* kind);          /* the ker
  * plain fields that may change between advance_until calls (src/gillespie_macro.rs:62-67); trajectories,
  * times and random streams are kept. */
 int rebop_batch_set_rates(rebop_batch* b, const double* k, size_t n_reactions);
+/* Watchdog: passes of the direct-method loop a trajectory may use per launch (0 = no limit).  A launch that hits it
+ * returns REBOP_ERR_ITER_CAP with everything kept on the device; repeating the same call (advance_until with the same
+ * tmax, run_grid with the same grid and saved species) continues every trajectory exactly where it stopped --
+ * finished trajectories are left alone, so the random streams stay those of an uninterrupted run. */
 int rebop_batch_set_max_iters(rebop_batch* b, uint32_t max_iters);
-/* How trajectories are mapped to SIMT lanes.  1 = static: thread n runs trajectory n, samples are staged in
- * shared memory and written as full 128-byte lines.  2 = dynamic: a resident grid, a lane whose trajectory is
- * finished claims the next one from a counter (no lane idles behind the slowest trajectory of its warp; samples
- * are stored one by one).  0 = auto.  Results are identical: every trajectory owns its state and random stream. */
+/* How trajectories are mapped to SIMT lanes.
+ *   1 = static: thread n runs trajectory n, samples are staged in shared memory and written as full 128-byte lines.
+ *   2, 3 = lanes claim trajectories: a resident grid, a lane whose trajectory is finished (or absorbed) claims the
+ *       next one from a counter, so no lane idles behind the slowest trajectory of its warp; every trajectory appends
+ *       its samples to a record of its own and a second kernel transposes the records into [step][row][trajectory]
+ *       (TMA bulk stores), converts them to the batch's sample type and leaves the row sums behind.
+ *       2 draws both random words of a pass ahead of the propensities (few samples per event), 3 draws the uniform
+ *       once the event is known to fire (many samples per event).
+ *   0 = auto (2 or 3 by an estimate of the events per sample).
+ * Results are identical: every trajectory owns its state and random stream. */
 int rebop_batch_set_schedule(rebop_batch* b, int schedule);
-int rebop_batch_get_schedule(const rebop_batch* b, int* schedule_used); /* of the last launch: 1 or 2 */    /* watchdog per launch; 0 = 2^32-1 */
+int rebop_batch_get_schedule(const rebop_batch* b, int* schedule_used); /* of the last launch: 1, 2 or 3 */
+/* Sample type of run_grid results from now on (rebop_sample_dtype; default REBOP_SAMPLES_I32). */
+int rebop_batch_set_sample_dtype(rebop_batch* b, int dtype);
+int rebop_batch_get_sample_dtype(const rebop_batch* b, int* dtype);
 /* Gillespie::seed (src/gillespie.rs:189-191) for every trajectory. */
 int rebop_batch_seed(rebop_batch* b, const uint64_t* seeds, uint64_t seed_base);
 /* get/set_time, get/set_species (src/gillespie.rs:246-267). species: [n_traj][n_species]. */
@@ -175,6 +196,9 @@ int rebop_batch_get_species(rebop_batch* b, int64_t* species);
 int rebop_batch_set_species(rebop_batch* b, const int64_t* species, int per_trajectory);
 /* Gillespie::advance_until (src/gillespie.rs:315-344) on every trajectory. */
 int rebop_batch_advance_until(rebop_batch* b, double tmax);
+/* Gillespie::advance_one_reaction (src/gillespie.rs:270-297) on every trajectory: exactly one pass of the direct
+ * method whatever the current time; a trajectory in an absorbing state gets t = +inf (:281-284). */
+int rebop_batch_advance_one_reaction(rebop_batch* b);
 /* The pyo3 grid loop (src/pyo3_gillespie.rs:197-208): for i in 0..=nb_steps
  * { advance_until(tmax*i/nb_steps); record species[save_idx] }.  save_idx: strictly increasing
  * species indices, or NULL for all species.
@@ -184,6 +208,14 @@ int rebop_batch_advance_until(rebop_batch* b, double tmax);
  * grid points, each copied to the host while the next is simulated (page-locked memory makes that overlap). */
 int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
                          uint32_t n_save, int32_t* host_out);
+/* Same for a batch of any sample type: host_out (optional) holds (nb_steps+1)*n_save*n_traj samples of the batch's
+ * sample type (rebop_batch_set_sample_dtype). */
+int rebop_batch_run_grid_typed(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
+                               uint32_t n_save, void* host_out);
+/* Same into a wider host array: row r of this batch goes to host_out[r * ld .. r * ld + n_traj) (elements of the
+ * batch's sample type), so the shards of an ensemble land side by side in one [step][save][all trajectories] array. */
+int rebop_batch_run_grid_strided(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
+                                 uint32_t n_save, void* host_out, size_t ld);
 /* The nb_steps = 0 path of the binding (src/pyo3_gillespie.rs:209-223) for every trajectory:
  * record; while t < tmax { _advance_one_reaction (src/gillespie.rs:275-297); record } -- one row per applied
  * reaction, the last one at or beyond tmax (t = +inf when the state became absorbing).  The log stays on the
@@ -193,16 +225,18 @@ int rebop_batch_run_events(rebop_batch* b, double tmax, const uint32_t* save_idx
 int rebop_batch_events_log_size(const rebop_batch* b, uint64_t* total_rows, uint32_t* n_save);
 /* offsets: [n_traj + 1], times: [total_rows], samples: [n_save][total_rows]; any of them may be NULL. */
 int rebop_batch_events_log_host(rebop_batch* b, uint64_t* offsets, double* times, int32_t* samples);
-/* Device view of the last run_grid's samples. */
-int rebop_batch_samples_device(const rebop_batch* b, const int32_t** dev_ptr, size_t* ld,
-                               uint32_t* n_rows);
-/* Copy the last run_grid's samples to the host: int32 or int64, [step][save][trajectory]. */
+/* Device view of the last run_grid's samples: [n_rows][ld] elements of the batch's sample type. */
+int rebop_batch_samples_device(const rebop_batch* b, const void** dev_ptr, size_t* ld, uint32_t* n_rows);
+/* Copy the last run_grid's samples to the host as [step][save][trajectory]: in the batch's own sample type, or as
+ * int32 / int64 whatever that type is (converted on the device, a chunk of rows at a time). */
+int rebop_batch_samples_host(rebop_batch* b, void* out);
 int rebop_batch_samples_host_i32(rebop_batch* b, int32_t* out);
 int rebop_batch_samples_host_i64(rebop_batch* b, int64_t* out);
 /* Same as _i32 into a wider host array: row r of this batch goes to out[r * ld .. r * ld + n_traj), so the
  * shards of an ensemble (one batch per GPU) land side by side in one [step][save][all trajectories] array
  * with no intermediate copy; out points at the first trajectory of this batch in row 0. */
 int rebop_batch_samples_host_i32_strided(rebop_batch* b, int32_t* out, size_t ld);
+int rebop_batch_samples_host_strided(rebop_batch* b, void* out, size_t ld); /* in the batch's own sample type */
 /* K4: per (step, saved species) sum and sum of squares over the trajectories of this batch,
  * as exact integers (so that sums over GPUs are order-independent). sum, sumsq: [n_rows]. */
 int rebop_batch_sample_sums(rebop_batch* b, int64_t* sum, uint64_t* sumsq);
@@ -214,16 +248,61 @@ int rebop_batch_events(rebop_batch* b, uint64_t* total, uint64_t* last_launch);
  * the fraction of SIMT lanes that applied a reaction (the rest idled on finished trajectories,
  * rejected ziggurat draws or grid crossings). */
 int rebop_batch_lane_slots(rebop_batch* b, uint64_t* last_launch);
-/* Device time of the last advance_until / run_grid launch in milliseconds (CUDA events). */
+/* Device time of the ensemble loop of the last advance_until / run_grid call in milliseconds (CUDA events on the
+ * batch's stream), and of the kernels that brought its samples into the result layout. */
 int rebop_batch_last_kernel_ms(rebop_batch* b, float* ms);
+int rebop_batch_last_finish_ms(rebop_batch* b, float* ms);
 int rebop_batch_size(const rebop_batch* b, size_t* n_traj);
-/* Block until the device has finished the batch's queued work. */
+/* Block until the device has finished the batch's queued work.  On a caller-owned stream (rebop_batch_set_stream)
+ * advance_until / run_grid / advance_one_reaction do not block the host; this call then reports what they would
+ * have (REBOP_ERR_ITER_CAP, REBOP_ERR_LIMIT) and accounts their events. */
 int rebop_batch_synchronize(rebop_batch* b);
 /* The CUDA stream (cudaStream_t / CUstream) every launch and copy of this batch is issued on, so
  * that a host framework can order its own work (events, collectives) against it. */
 int rebop_batch_get_stream(const rebop_batch* b, void** stream);
 /* Issue this batch's work on a caller-owned stream instead (NULL restores the batch's own). */
 int rebop_batch_set_stream(rebop_batch* b, void* stream);
+
+/* ---- one ensemble over several GPUs of one node ---- */
+
+/* N trajectories sharded over `devices` in contiguous ranges [g*N/G, (g+1)*N/G): one batch per device, one host
+ * worker thread per device for the duration of a call, no data-path collective (trajectories are independent; the
+ * reference's only ensemble is the host loop of examples/sir.rs:11-22).  Every trajectory carries its own seed
+ * (seeds[n], or seed_base + n), so results do not depend on the number of devices.  Arguments as for
+ * rebop_batch_create, indexed over the whole ensemble. */
+typedef struct rebop_ensemble rebop_ensemble;
+int rebop_ensemble_create(const rebop_network* net, const int* devices, int n_devices, size_t n_traj, const int64_t* x0,
+                          int x0_per_trajectory, const uint64_t* seeds, uint64_t seed_base, rebop_ensemble** out);
+void rebop_ensemble_destroy(rebop_ensemble* e);
+int rebop_ensemble_size(const rebop_ensemble* e, size_t* n_traj);
+int rebop_ensemble_shards(const rebop_ensemble* e, int* n_shards);
+/* The batch of shard g (owned by the ensemble; NULL if its range is empty), its device and trajectory range. */
+int rebop_ensemble_shard(const rebop_ensemble* e, int g, rebop_batch** batch, int* device, size_t* first, size_t* count);
+/* The batch setters and steppers of the same name, applied to every shard concurrently. */
+int rebop_ensemble_set_kernel(rebop_ensemble* e, int kind);
+int rebop_ensemble_set_schedule(rebop_ensemble* e, int schedule);
+int rebop_ensemble_set_sample_dtype(rebop_ensemble* e, int dtype);
+int rebop_ensemble_set_max_iters(rebop_ensemble* e, uint32_t max_iters);
+int rebop_ensemble_set_rates(rebop_ensemble* e, const double* k, size_t n_reactions);
+int rebop_ensemble_set_time(rebop_ensemble* e, double t);
+int rebop_ensemble_set_species(rebop_ensemble* e, const int64_t* species, int per_trajectory);
+int rebop_ensemble_seed(rebop_ensemble* e, const uint64_t* seeds, uint64_t seed_base);
+int rebop_ensemble_advance_until(rebop_ensemble* e, double tmax);
+int rebop_ensemble_advance_one_reaction(rebop_ensemble* e);
+/* rebop_batch_run_grid on every shard; host_out (optional): [step][save][all n_traj trajectories] in the ensemble's
+ * sample type, every shard writing its own columns. */
+int rebop_ensemble_run_grid(rebop_ensemble* e, double tmax, uint32_t nb_steps, const uint32_t* save_idx, uint32_t n_save,
+                            void* host_out);
+int rebop_ensemble_samples_host(rebop_ensemble* e, void* out);
+/* Ensemble statistics of the last run_grid per (step, saved species): every device reduces its shard to exact int64
+ * sums and sums of squares, ncclAllReduce(ncclInt64, ncclSum) over an ncclCommInitAll communicator combines them (no
+ * NCCL call with one device), and a device kernel turns them into mean and unbiased variance with 128-bit integer
+ * arithmetic.  Integer sums make the result independent of the device count and of the reduction order.
+ * NCCL is opened with dlopen (REBOP_B200_NCCL_LIB overrides the path); REBOP_ERR_NCCL if it is missing. */
+int rebop_ensemble_stats(rebop_ensemble* e, double* mean, double* var);
+int rebop_ensemble_sums(rebop_ensemble* e, int64_t* sum, uint64_t* sumsq);
+int rebop_ensemble_events(rebop_ensemble* e, uint64_t* total, uint64_t* last_call);
+int rebop_ensemble_last_kernel_ms(rebop_ensemble* e, float* max_ms);
 
 /* ---- host memory ---- */
 

@@ -160,6 +160,18 @@ class Network:
         xa = np.ascontiguousarray(x, dtype=np.int64)
         return float(lib().ora_rate(self._h, r, _p(xa, C.c_int64)))
 
+    def step_one(self, x0, seed: int, n_steps: int, t0: float = 0.0):
+        """n_steps calls of Gillespie::advance_one_reaction (src/gillespie.rs:270-297) -> (t, x[S], events)."""
+        x = np.ascontiguousarray(x0, dtype=np.int64).copy()
+        st = State()
+        st.x = _p(x, C.c_int64)
+        st.t = float(t0)
+        st.events = 0
+        lib().ora_rng_seed(C.byref(st.rng), C.c_uint64(int(seed)))
+        for _ in range(n_steps):
+            lib().ora_advance_one_reaction(self._h, C.byref(st))
+        return float(st.t), x, int(st.events)
+
     def run_grid(self, x0, seed: int, tmax: float, nb_steps: int, save_idx=None):
         """pyo3 grid loop for one trajectory -> (times[nb+1], out[nb+1][n_save], events)."""
         x0a = np.ascontiguousarray(x0, dtype=np.int64)

@@ -9,12 +9,16 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-import numpy as np
+import numpy as np  # noqa: E402  (used by the constants below)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librebop_b200.so")
 
-OK, ERR_INVALID, ERR_OUT_OF_RANGE, ERR_PARSE, ERR_MISSING_PARAM, ERR_CUDA, ERR_NVRTC, ERR_LIMIT, ERR_ITER_CAP = range(9)
+(OK, ERR_INVALID, ERR_OUT_OF_RANGE, ERR_PARSE, ERR_MISSING_PARAM, ERR_CUDA, ERR_NVRTC, ERR_LIMIT, ERR_ITER_CAP,
+ ERR_NCCL) = range(10)
+SAMPLES_I16, SAMPLES_I32, SAMPLES_I64 = 2, 4, 8
+SAMPLE_DTYPES = {2: np.int16, 4: np.int32, 8: np.int64}
+SCHEDULE_AUTO, SCHEDULE_STATIC, SCHEDULE_SPARSE, SCHEDULE_DENSE = 0, 1, 2, 3
 ARITH_API, ARITH_MACRO = 0, 1
 KERNEL_AUTO, KERNEL_TABLE, KERNEL_NVRTC, KERNEL_PREBUILT = 0, 1, 2, 3
 OPCODES = dict(const=0, species=1, neg=2, add=3, sub=4, mul=5, div=6, pow=7, max=8, min=9, exp=10)
@@ -96,6 +100,14 @@ SIGNATURES = {
     "rebop_batch_get_species": (C.c_int, [_vp, _i64p]),
     "rebop_batch_set_species": (C.c_int, [_vp, _i64p, C.c_int]),
     "rebop_batch_advance_until": (C.c_int, [_vp, C.c_double]),
+    "rebop_batch_advance_one_reaction": (C.c_int, [_vp]),
+    "rebop_batch_set_sample_dtype": (C.c_int, [_vp, C.c_int]),
+    "rebop_batch_get_sample_dtype": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "rebop_batch_run_grid_typed": (C.c_int, [_vp, C.c_double, C.c_uint32, _u32p, C.c_uint32, _vp]),
+    "rebop_batch_run_grid_strided": (C.c_int, [_vp, C.c_double, C.c_uint32, _u32p, C.c_uint32, _vp, C.c_size_t]),
+    "rebop_batch_samples_host": (C.c_int, [_vp, _vp]),
+    "rebop_batch_samples_host_strided": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "rebop_batch_last_finish_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rebop_batch_run_grid": (C.c_int, [_vp, C.c_double, C.c_uint32, _u32p, C.c_uint32, _i32p]),
     "rebop_batch_run_events": (C.c_int, [_vp, C.c_double, _u32p, C.c_uint32]),
     "rebop_batch_events_log_size": (C.c_int, [_vp, _u64p, _u32p]),
@@ -113,6 +125,27 @@ SIGNATURES = {
     "rebop_batch_synchronize": (C.c_int, [_vp]),
     "rebop_batch_get_stream": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
     "rebop_batch_set_stream": (C.c_int, [_vp, _vp]),
+    "rebop_ensemble_create": (C.c_int, [_vp, C.POINTER(C.c_int), C.c_int, C.c_size_t, _i64p, C.c_int, _u64p, C.c_uint64, _pp]),
+    "rebop_ensemble_destroy": (None, [_vp]),
+    "rebop_ensemble_size": (C.c_int, [_vp, _szp]),
+    "rebop_ensemble_shards": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "rebop_ensemble_shard": (C.c_int, [_vp, C.c_int, _pp, C.POINTER(C.c_int), _szp, _szp]),
+    "rebop_ensemble_set_kernel": (C.c_int, [_vp, C.c_int]),
+    "rebop_ensemble_set_schedule": (C.c_int, [_vp, C.c_int]),
+    "rebop_ensemble_set_sample_dtype": (C.c_int, [_vp, C.c_int]),
+    "rebop_ensemble_set_max_iters": (C.c_int, [_vp, C.c_uint32]),
+    "rebop_ensemble_set_rates": (C.c_int, [_vp, _f64p, C.c_size_t]),
+    "rebop_ensemble_set_time": (C.c_int, [_vp, C.c_double]),
+    "rebop_ensemble_set_species": (C.c_int, [_vp, _i64p, C.c_int]),
+    "rebop_ensemble_seed": (C.c_int, [_vp, _u64p, C.c_uint64]),
+    "rebop_ensemble_advance_until": (C.c_int, [_vp, C.c_double]),
+    "rebop_ensemble_advance_one_reaction": (C.c_int, [_vp]),
+    "rebop_ensemble_run_grid": (C.c_int, [_vp, C.c_double, C.c_uint32, _u32p, C.c_uint32, _vp]),
+    "rebop_ensemble_samples_host": (C.c_int, [_vp, _vp]),
+    "rebop_ensemble_stats": (C.c_int, [_vp, _f64p, _f64p]),
+    "rebop_ensemble_sums": (C.c_int, [_vp, _i64p, _u64p]),
+    "rebop_ensemble_events": (C.c_int, [_vp, _u64p, _u64p]),
+    "rebop_ensemble_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rebop_b200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "rebop_b200_host_free": (C.c_int, [_vp]),
     "rebop_b200_kernel_launches": (C.c_uint64, []),
@@ -354,7 +387,8 @@ class Batch:
         check(lib.rebop_batch_set_rates(self._h, ptr(k, C.c_double), k.size))
 
     def set_schedule(self, schedule: int) -> None:
-        """0 auto, 1 static, 2 dynamic (see rebop_batch_set_schedule)."""
+        """0 auto, 1 static, 2 lanes claim trajectories (sparse samples), 3 the same for dense samples
+        (see rebop_batch_set_schedule)."""
         check(lib.rebop_batch_set_schedule(self._h, int(schedule)))
 
     @property
@@ -376,6 +410,19 @@ class Batch:
     def advance_until(self, tmax: float) -> None:
         check(lib.rebop_batch_advance_until(self._h, float(tmax)))
 
+    def advance_one_reaction(self) -> None:
+        check(lib.rebop_batch_advance_one_reaction(self._h))
+
+    def set_sample_dtype(self, dtype) -> None:
+        """Sample type of run_grid results: np.int16, np.int32 (default) or np.int64."""
+        check(lib.rebop_batch_set_sample_dtype(self._h, int(np.dtype(dtype).itemsize)))
+
+    @property
+    def sample_dtype(self):
+        v = C.c_int()
+        check(lib.rebop_batch_get_sample_dtype(self._h, C.byref(v)))
+        return np.dtype(SAMPLE_DTYPES[v.value])
+
     def run_grid(self, tmax: float, nb_steps: int, save_idx=None, host_out: np.ndarray | None = None) -> None:
         n_save = self.net.n_species if save_idx is None else len(save_idx)
         sp = None
@@ -384,23 +431,27 @@ class Batch:
             sp = ptr(sv, C.c_uint32)
         hp = None
         if host_out is not None:
-            assert host_out.dtype == np.int32 and host_out.flags.c_contiguous
+            assert host_out.dtype == self.sample_dtype and host_out.flags.c_contiguous
             assert host_out.size == (nb_steps + 1) * n_save * self.n_traj
-            hp = ptr(host_out, C.c_int32)
+            hp = C.c_void_p(host_out.ctypes.data)
         self.rows, self.n_save = (nb_steps + 1) * n_save, n_save
-        check(lib.rebop_batch_run_grid(self._h, float(tmax), int(nb_steps), sp, n_save, hp))
+        check(lib.rebop_batch_run_grid_typed(self._h, float(tmax), int(nb_steps), sp, n_save, hp))
 
-    def samples(self, dtype=np.int32) -> np.ndarray:
-        """Samples of the last run_grid as [nb_steps+1][n_save][n_traj]."""
+    def samples(self, dtype=None) -> np.ndarray:
+        """Samples of the last run_grid as [nb_steps+1][n_save][n_traj]: in the batch's sample type by default, or
+        as int32 / int64 (converted on the device)."""
         steps = self.rows // self.n_save if self.n_save else 0
+        dtype = self.sample_dtype if dtype is None else np.dtype(dtype)
         out = np.empty((steps, self.n_save, self.n_traj), dtype=dtype)
         if out.size:
-            if dtype == np.int32:
+            if dtype == self.sample_dtype:
+                check(lib.rebop_batch_samples_host(self._h, C.c_void_p(out.ctypes.data)))
+            elif dtype == np.int32:
                 check(lib.rebop_batch_samples_host_i32(self._h, ptr(out, C.c_int32)))
             elif dtype == np.int64:
                 check(lib.rebop_batch_samples_host_i64(self._h, ptr(out, C.c_int64)))
             else:
-                raise TypeError("dtype must be int32 or int64")
+                raise TypeError("dtype must be the batch's sample type, int32 or int64")
         return out
 
     def run_events(self, tmax: float, save_idx=None):
@@ -425,11 +476,11 @@ class Batch:
     def samples_into(self, out: np.ndarray, first: int) -> None:
         """Write the samples into columns [first, first + n_traj) of a C-contiguous int32 array
         [nb_steps+1][n_save][n_total] (no intermediate copy)."""
-        assert out.dtype == np.int32 and out.flags.c_contiguous and out.ndim == 3
+        assert out.dtype == self.sample_dtype and out.flags.c_contiguous and out.ndim == 3
         assert out.shape[0] * out.shape[1] == self.rows and first + self.n_traj <= out.shape[2]
         if out.size:
-            base = out.ctypes.data + 4 * first
-            check(lib.rebop_batch_samples_host_i32_strided(self._h, C.cast(base, _i32p), out.shape[2]))
+            base = out.ctypes.data + out.dtype.itemsize * first
+            check(lib.rebop_batch_samples_host_strided(self._h, C.c_void_p(base), out.shape[2]))
 
     def samples_device(self):
         """(device pointer, leading dimension in elements, rows) of the last run_grid's samples."""
@@ -484,6 +535,13 @@ class Batch:
         check(lib.rebop_batch_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
 
+    @property
+    def last_finish_ms(self) -> float:
+        """Device time of the kernels that brought the last run_grid's samples into the result layout."""
+        ms = C.c_float()
+        check(lib.rebop_batch_last_finish_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def synchronize(self) -> None:
         check(lib.rebop_batch_synchronize(self._h))
 
@@ -496,6 +554,148 @@ class Batch:
 
     def set_stream(self, stream: int | None) -> None:
         check(lib.rebop_batch_set_stream(self._h, C.c_void_p(stream or None)))
+
+
+class Ensemble:
+    """Owning wrapper of a rebop_ensemble handle: N trajectories sharded over several GPUs of this node (one process,
+    one batch and one host worker thread per device; NCCL only for the ensemble statistics)."""
+
+    def __init__(self, net: Network, n_traj: int, x0, devices, seeds=None, seed_base: int = 0, kernel: int = KERNEL_AUTO,
+                 dtype=np.int32):
+        x0a = np.ascontiguousarray(x0, dtype=np.int64)
+        per_traj = 1 if x0a.ndim == 2 else 0
+        if per_traj and x0a.shape != (n_traj, net.n_species):
+            raise RebopError(ERR_INVALID, "x0 must be [n_species] or [n_traj][n_species]")
+        if not per_traj and x0a.shape != (net.n_species,):
+            raise RebopError(ERR_INVALID, "assertion failed: species.len() == nb_species")
+        sp = None
+        if seeds is not None:
+            self._seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+            if self._seeds.shape != (n_traj,):
+                raise RebopError(ERR_INVALID, "seeds must have one entry per trajectory")
+            sp = ptr(self._seeds, C.c_uint64)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        check(lib.rebop_ensemble_create(net._h, devs, len(devices), int(n_traj), ptr(x0a, C.c_int64) if x0a.size else None, per_traj,
+                                        sp, C.c_uint64(int(seed_base) & (2**64 - 1)), C.byref(h)))
+        self._h = h
+        self.net = net
+        self.n_traj = int(n_traj)
+        self.devices = [int(d) for d in devices]
+        self.rows = 0
+        self.n_save = 0
+        self.dtype = np.dtype(dtype)
+        if kernel != KERNEL_AUTO:
+            check(lib.rebop_ensemble_set_kernel(self._h, int(kernel)))
+        if self.dtype != np.int32:
+            check(lib.rebop_ensemble_set_sample_dtype(self._h, int(self.dtype.itemsize)))
+
+    def __del__(self):
+        self.close()
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.rebop_ensemble_destroy(self._h)
+            self._h = None
+
+    def shards(self):
+        """[(device, first, count)] -- the contiguous trajectory range of every device."""
+        n = C.c_int()
+        check(lib.rebop_ensemble_shards(self._h, C.byref(n)))
+        out = []
+        for g in range(n.value):
+            dev, first, count = C.c_int(), C.c_size_t(), C.c_size_t()
+            check(lib.rebop_ensemble_shard(self._h, g, None, C.byref(dev), C.byref(first), C.byref(count)))
+            out.append((dev.value, first.value, count.value))
+        return out
+
+    def set_schedule(self, schedule: int) -> None:
+        check(lib.rebop_ensemble_set_schedule(self._h, int(schedule)))
+
+    def set_max_iters(self, n: int) -> None:
+        check(lib.rebop_ensemble_set_max_iters(self._h, int(n)))
+
+    def set_time(self, t: float) -> None:
+        check(lib.rebop_ensemble_set_time(self._h, float(t)))
+
+    def set_species(self, species) -> None:
+        a = np.ascontiguousarray(species, dtype=np.int64)
+        check(lib.rebop_ensemble_set_species(self._h, ptr(a, C.c_int64), 1 if a.ndim == 2 else 0))
+
+    def seed(self, seeds=None, seed_base: int = 0) -> None:
+        if seeds is None:
+            check(lib.rebop_ensemble_seed(self._h, None, C.c_uint64(int(seed_base))))
+        else:
+            s = np.ascontiguousarray(seeds, dtype=np.uint64)
+            check(lib.rebop_ensemble_seed(self._h, ptr(s, C.c_uint64), 0))
+
+    def advance_until(self, tmax: float) -> None:
+        check(lib.rebop_ensemble_advance_until(self._h, float(tmax)))
+
+    def run_grid(self, tmax: float, nb_steps: int, save_idx=None, host_out: np.ndarray | None = None) -> None:
+        n_save = self.net.n_species if save_idx is None else len(save_idx)
+        sp = None
+        if save_idx is not None:
+            sv = np.ascontiguousarray(save_idx, dtype=np.uint32)
+            sp = ptr(sv, C.c_uint32)
+        hp = None
+        if host_out is not None:
+            assert host_out.dtype == self.dtype and host_out.flags.c_contiguous
+            assert host_out.size == (nb_steps + 1) * n_save * self.n_traj
+            hp = C.c_void_p(host_out.ctypes.data)
+        self.rows, self.n_save = (nb_steps + 1) * n_save, n_save
+        check(lib.rebop_ensemble_run_grid(self._h, float(tmax), int(nb_steps), sp, n_save, hp))
+
+    def samples(self) -> np.ndarray:
+        steps = self.rows // self.n_save if self.n_save else 0
+        out = np.empty((steps, self.n_save, self.n_traj), dtype=self.dtype)
+        if out.size:
+            check(lib.rebop_ensemble_samples_host(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def stats(self):
+        """(mean, unbiased variance) per (step, saved species): K4 per device, NCCL all-reduce, device finalisation."""
+        mean = np.zeros(self.rows, dtype=np.float64)
+        var = np.zeros(self.rows, dtype=np.float64)
+        check(lib.rebop_ensemble_stats(self._h, ptr(mean, C.c_double), ptr(var, C.c_double)))
+        steps = self.rows // self.n_save if self.n_save else 0
+        return mean.reshape(steps, self.n_save), var.reshape(steps, self.n_save)
+
+    def sums(self):
+        s1 = np.zeros(self.rows, dtype=np.int64)
+        s2 = np.zeros(self.rows, dtype=np.uint64)
+        check(lib.rebop_ensemble_sums(self._h, ptr(s1, C.c_int64), ptr(s2, C.c_uint64)))
+        return s1, s2
+
+    def events(self):
+        tot, last = C.c_uint64(), C.c_uint64()
+        check(lib.rebop_ensemble_events(self._h, C.byref(tot), C.byref(last)))
+        return tot.value, last.value
+
+    @property
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(lib.rebop_ensemble_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+
+def _find_nccl() -> None:
+    """Point the library's dlopen at the NCCL that ships with the nvidia-nccl wheel when the system has none on the
+    loader path (the C ABI honours REBOP_B200_NCCL_LIB)."""
+    if os.environ.get("REBOP_B200_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["REBOP_B200_NCCL_LIB"] = cand
+    except (ImportError, ValueError):
+        pass
+
+
+_find_nccl()
 
 
 def kernel_launches() -> int:

@@ -64,8 +64,9 @@ std::string emit_expr(const std::vector<rebop_expr_op>& prog) {
 static void emit_kernels(std::ostringstream& o, const std::string& kernel_name, unsigned block, unsigned minctas, int variant) {
   struct Entry { const char* suffix; const char* body; int in; };
   const Entry entries[] = {
-      {"", "rb_ssa_loop<RbGenNet, false>(net, p, rb_smem);", RB_VARIANT_GRID},
-      {"_dyn", "rb_ssa_loop<RbGenNet, true>(net, p, rb_smem);", RB_VARIANT_GRID},
+      {"", "rb_ssa_loop<RbGenNet, RB_MODE_STATIC>(net, p, rb_smem);", RB_VARIANT_GRID},
+      {"_dyn", "rb_ssa_loop<RbGenNet, RB_MODE_SPARSE>(net, p, rb_smem);", RB_VARIANT_GRID},
+      {"_dns", "rb_ssa_loop<RbGenNet, RB_MODE_DENSE>(net, p, rb_smem);", RB_VARIANT_GRID},
       {"_evc", "rb_ssa_events<RbGenNet, false>(net, p, rb_smem);", RB_VARIANT_EVENTS},
       {"_evw", "rb_ssa_events<RbGenNet, true>(net, p, rb_smem);", RB_VARIANT_EVENTS},
   };
@@ -193,9 +194,9 @@ static std::string large_source(const rebop_network& net, const std::string& ker
   else o << "    return rb_large_select<" << nck << ", " << ckn << ", " << R << ", " << (macro ? "true" : "false")
          << ", BLOCK>(ck, chosen, xs, p.gtab);\n";
   o << "  }\n";
-  o << "  __device__ __forceinline__ bool apply(const SsaRunParams& p, int pick) {\n";
-  if (R == 0) o << "    return false;\n";
-  else o << "    return rb_large_apply<" << R << ", BLOCK>(pick, xs, p.gtab);\n";
+  o << "  __device__ __forceinline__ void apply(const SsaRunParams& p, int pick, rb_u32& nev) {\n";
+  if (R == 0) o << "    (void)pick; (void)nev;\n";
+  else o << "    if (rb_large_apply<" << R << ", BLOCK>(pick, xs, p.gtab)) ++nev;\n";
   o << "  }\n";
   o << "  static __device__ __forceinline__ int none() { return " << R << "; }\n";
   o << "  __device__ __forceinline__ void record(const SsaRunParams& p, int* dst, rb_u32 stride) const {\n";
@@ -217,9 +218,10 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   for (const RbReaction& rx : net.rx)
     for (int64_t d : rx.diff)
       if (d < -127 || d > 127) wide = true;
+  // lane S of every row counts the event: 1 for a reaction, 0 for the all-zero "no reaction" row, so that the
+  // event counter is updated by the same instruction kind as the species (no test of the pick in the loop)
   const int per_word = wide ? 2 : 4;
-  int dw = (S + per_word - 1) / per_word;
-  if (dw == 0) dw = 1;
+  int dw = (S + 1 + per_word - 1) / per_word;
   int dwp = dw <= 2 ? dw : (dw + 3) / 4 * 4;  // 1, 2 or a multiple of 4 words per reaction
   std::vector<bool> touched(S, false);
   for (const RbReaction& rx : net.rx)
@@ -270,8 +272,8 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
       unsigned word = 0;
       for (int l = 0; l < per_word; ++l) {
         const int s = w * per_word + l;
-        if (s >= S) continue;
-        const long long d = net.rx[r].diff[s];
+        if (s > S) continue;
+        const long long d = s == S ? 1 : net.rx[r].diff[s];
         if (wide) word |= ((unsigned)(d & 0xffff)) << (16 * l);
         else word |= ((unsigned)(d & 0xff)) << (8 * l);
       }
@@ -362,8 +364,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   o << "  __device__ __forceinline__ int select(const SsaRunParams&, double chosen) const {\n";
   if (R == 0) {
     o << "    return 0;\n  }\n";
-    o << "  __device__ __forceinline__ bool apply(const SsaRunParams&, int) {\n";
-    o << "    return false;\n";
+    o << "  __device__ __forceinline__ void apply(const SsaRunParams&, int, rb_u32&) {\n";
   } else {
     if (!macro) {
       // choose_cumrate_sum (src/gillespie.rs:402-407): index = number of cum < chosen (two
@@ -387,7 +388,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
     o << "    return i;\n  }\n";
     // row R of the table is all zeros: applying it is the branch-free \"no reaction\" (macro arithmetic: nothing
     // matched, src/gillespie_macro.rs:150-171; any arithmetic: the ensemble loop's lanes without an event)
-    o << "  __device__ __forceinline__ bool apply(const SsaRunParams& p, int i) {\n";
+    o << "  __device__ __forceinline__ void apply(const SsaRunParams& p, int i, rb_u32& nev) {\n";
     // fetch the packed stoichiometry row of reaction i from shared memory
     if (dwp == 1) {
       o << "    const int w0 = rb_lds_i32(tab + 4u * i);\n";
@@ -409,8 +410,12 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
         o << "    rb_bias_dp4a(x[" << s << "], w" << w << ", p.byte_sel[" << l << "]);\n";
       }
     }
+    {
+      const int w = S / per_word, l = S % per_word;
+      if (wide) o << "    nev = (rb_u32)__dp2a_lo(w" << w << ", " << (l ? "0x100" : "0x1") << ", (int)nev);\n";
+      else o << "    nev = (rb_u32)__dp4a(w" << w << ", p.byte_sel[" << l << "], (int)nev);\n";
+    }
     for (int w = 0; w < dwp; ++w) o << "    (void)w" << w << ";\n";
-    o << "    return i != " << R << ";\n";
   }
   o << "  }\n";
 

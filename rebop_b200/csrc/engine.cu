@@ -16,6 +16,7 @@
 
 #include "jit.hpp"
 #include "network.hpp"
+#include "samples.h"
 #include "ssa_params.h"
 #include "ssa_table.h"
 
@@ -34,31 +35,55 @@ struct rebop_batch {
   int device = 0;
   size_t n = 0, ldn = 0;
   int* d_x = nullptr;
+  int* d_x0 = nullptr;  // [S] staging of a broadcast initial state
   double* d_t = nullptr;
   rb_u64* d_rng = nullptr;
   rb_u64* d_seeds = nullptr;
   rb_u64 seed_base = 0;
   unsigned seed_mode = 0;  // pending seeding for the next launch (0 = streams already live)
-  int* d_out = nullptr;
-  size_t out_capacity = 0;  // int32 elements
+  void* d_out = nullptr;    // samples [rows][ldn] in the batch's sample type; event-log mode: int32 [n_save][total_rows]
+  size_t out_capacity = 0;  // bytes
+  int sample_bytes = 4;     // REBOP_SAMPLES_*: 2, 4 or 8
+  int* d_raw = nullptr;     // lanes-claim-trajectories schedules: per-trajectory records [n][points][n_save] (see samples.cu)
+  size_t raw_capacity = 0;  // int32 elements
+  int* d_stat32 = nullptr;  // static schedule with a sample type other than int32: the kernel's int32 rows before conversion
+  size_t stat32_capacity = 0;
+  rb_u32* d_progress = nullptr;  // [ldn] RB_PROGRESS_*
   uint32_t out_rows = 0;    // (nb_steps+1) * n_save of the last run_grid
   uint32_t out_n_save = 0, out_nb_steps = 0;
   rb_u64* d_counters = nullptr;  // [0] events, [1] status (low 32 bits), [2] lane slots
+  rb_u64* h_counters = nullptr;  // page-locked mirror (asynchronous launches report through it)
   rb_i64* d_sums = nullptr;
   size_t sums_capacity = 0;
+  bool sums_ready = false;       // d_sums holds the row sums of the current samples (fused into the finishing kernel)
+  bool async_pending = false;    // a launch on a caller-owned stream has not been accounted for yet
+  RbTables* d_tables = nullptr;  // table-driven kernel: this batch's network image on the device
+  bool tables_uploaded = false;
+  // a call cut short by the watchdog (REBOP_ERR_ITER_CAP): repeating it with the same arguments continues it
+  struct Pending {
+    bool active = false;
+    int kind = 0;  // 0 advance_until, 1 run_grid
+    double tmax = 0.0;
+    uint32_t nb_steps = 0, n_save = 0;
+    std::vector<uint32_t> save;
+    unsigned segment = 0;  // run_grid: first segment that is not complete
+    uint64_t events = 0, lane_slots = 0;
+    float ms = 0.f;
+  } pend;
   cudaStream_t stream = nullptr;      // the stream work is issued on
   cudaStream_t own_stream = nullptr;  // created with the batch; `stream` may point elsewhere
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;  // around the ensemble loop (ev0, ev1) and the sample finishing (ev1, ev2)
   uint64_t events_total = 0, events_last = 0, lane_slots_last = 0;
   int kernel_pref = REBOP_KERNEL_AUTO, kernel_used = REBOP_KERNEL_AUTO;
   uint32_t max_iters = 0;
-  float last_ms = 0.f;
+  float last_ms = 0.f, last_finish_ms = 0.f;
   RbTables tables;
   bool tables_ok = false;
   std::string tables_error;
   int max_smem_optin = 0, sm_count = 0;
-  int schedule = 0;               // 0 auto, 1 static (ring-staged coalesced samples), 2 dynamic (lanes claim trajectories)
-  bool dynamic_last = false;
+  int schedule = 0;               // 0 auto, 1 static (ring-staged coalesced samples), 2 lanes claim trajectories (sparse
+                                  // samples), 3 lanes claim trajectories (dense samples)
+  int mode_last = RB_MODE_STATIC;
   std::vector<int64_t> x_first;   // counts of the first trajectory as last uploaded (schedule heuristic)
   bool x_nonneg = true;           // every count uploaded so far was >= 0 (large specialised kernels need it)
   rb_u32* d_gtab = nullptr;       // large specialised kernels: reaction records + saved-species list
@@ -72,6 +97,8 @@ struct rebop_batch {
   rb_u64* d_ev_offsets = nullptr;
   double* d_ev_times = nullptr;
   size_t ev_times_capacity = 0;
+  int* d_ev_out = nullptr;  // int32 [n_save][total_rows]
+  size_t ev_out_capacity = 0;
   std::vector<uint64_t> ev_offsets;  // [n + 1] after run_events
   uint32_t ev_n_save = 0;
 };
@@ -86,6 +113,16 @@ __global__ void rb_fill_state_kernel(int* x, double* t, const int* x0, unsigned 
   if (fill_x)
     for (unsigned s = 0; s < n_species; ++s) x[(size_t)s * ldn + i] = i < n ? x0[s] : 0;
   if (fill_t) t[i] = t0;
+}
+
+// get_species: x[S][ldn] int32 -> rows [n][S] int64 (the layout the C ABI returns), transposed on the device.
+__global__ void rb_species_rows_kernel(const int* __restrict__ x, long long* __restrict__ rows, unsigned n_species, unsigned ldn,
+                                       unsigned n) {
+  const size_t total = (size_t)n * n_species;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned traj = (unsigned)(i / n_species), sp = (unsigned)(i - (size_t)traj * n_species);
+    rows[i] = x[(size_t)sp * ldn + traj];
+  }
 }
 
 // K5: SmallRng::seed_from_u64 for every trajectory (src/gillespie.rs:184,190): SplitMix64 fills the xoshiro256++
@@ -104,26 +141,33 @@ __global__ void rb_seed_kernel(rb_u64* rng, const rb_u64* seeds, rb_u64 seed_bas
   }
 }
 
-// K4: exact integer sum and sum of squares of every sample row over the trajectories.
-// rows are 128-byte aligned (ldn % 32 == 0); one CTA reduces a segment of one row.
-__global__ void __launch_bounds__(256) rb_row_sums_kernel(const int* __restrict__ samples, unsigned n,
-                                                          unsigned ldn, rb_i64* __restrict__ sums,
-                                                          unsigned n_rows) {
-  const unsigned row = blockIdx.y;
-  const int4* src = reinterpret_cast<const int4*>(samples + (size_t)row * ldn);
-  const unsigned n4 = n / 4u;
+// K4: exact integer sum and sum of squares of every sample row over the trajectories, for samples of any of the three
+// sample types (the claiming schedules get these sums from the finishing kernel; this one serves the static schedule).
+// rows are 128-byte aligned (ldn % 32 == 0); one CTA reduces a segment of one row with 16-byte loads.
+template <typename T>
+__global__ void __launch_bounds__(256) rb_row_sums_kernel(const T* __restrict__ samples, unsigned n, unsigned ldn,
+                                                          rb_i64* __restrict__ sums, unsigned n_rows) {
+  constexpr unsigned per = 16u / (unsigned)sizeof(T);
+  const unsigned row = blockIdx.x;  // rows on x: (nb_steps + 1) * n_save may exceed the 65535 limit of the other grid dimensions
+  const T* base = samples + (size_t)row * ldn;
+  const int4* src = reinterpret_cast<const int4*>(base);
+  const unsigned nv = n / per;
   rb_i64 s1 = 0;
   rb_u64 s2 = 0;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+  for (unsigned i = blockIdx.y * blockDim.x + threadIdx.x; i < nv; i += gridDim.y * blockDim.x) {
     const int4 v = __ldcs(src + i);
-    s1 += (rb_i64)v.x + v.y + v.z + v.w;
-    s2 += (rb_u64)((rb_i64)v.x * v.x) + (rb_u64)((rb_i64)v.y * v.y) + (rb_u64)((rb_i64)v.z * v.z) +
-          (rb_u64)((rb_i64)v.w * v.w);
+    const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (unsigned j = 0; j < per; ++j) {
+      const rb_i64 x = (rb_i64)e[j];
+      s1 += x;
+      s2 += (rb_u64)(x * x);
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) {
-    const int v = samples[(size_t)row * ldn + n4 * 4u + threadIdx.x];
-    s1 += v;
-    s2 += (rb_u64)((rb_i64)v * v);
+  if (blockIdx.y == 0 && threadIdx.x < n - nv * per) {
+    const rb_i64 x = (rb_i64)base[nv * per + threadIdx.x];
+    s1 += x;
+    s2 += (rb_u64)(x * x);
   }
   for (int off = 16; off > 0; off >>= 1) {
     s1 += __shfl_down_sync(0xffffffffu, s1, off);
@@ -143,6 +187,18 @@ __global__ void __launch_bounds__(256) rb_row_sums_kernel(const int* __restrict_
     }
     atomicAdd(reinterpret_cast<rb_u64*>(sums) + row, (rb_u64)s1);
     atomicAdd(reinterpret_cast<rb_u64*>(sums) + n_rows + row, s2);
+  }
+}
+
+// Sample rows [rows][ldn] of one sample type into dense rows [rows][n] of another (the widening / narrowing the
+// host accessors offer, done on the device instead of in a host loop).
+template <typename In, typename Out>
+__global__ void __launch_bounds__(256) rb_rows_retype_kernel(const In* __restrict__ in, Out* __restrict__ out, unsigned n,
+                                                             unsigned ldn, unsigned rows) {
+  const size_t total = (size_t)rows * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / n;
+    out[i] = (Out)in[r * ldn + (i - r * n)];
   }
 }
 
@@ -221,22 +277,19 @@ static int upload_x0(rebop_batch* b, const int64_t* x0, int per_traj) {
   if (!per_traj) {
     std::vector<int> h(S);
     for (uint32_t s = 0; s < S; ++s) h[s] = (int)x0[s];
-    int* d_x0 = nullptr;
-    RB_CUDA(cudaMallocAsync(&d_x0, S * sizeof(int), b->stream));
-    RB_CUDA(cudaMemcpyAsync(d_x0, h.data(), S * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    // a copy from pageable memory returns once the source has been staged, so `h` may go out of scope
+    RB_CUDA(cudaMemcpyAsync(b->d_x0, h.data(), S * sizeof(int), cudaMemcpyHostToDevice, b->stream));
     rb_fill_state_kernel<<<(unsigned)((b->ldn + 255) / 256), 256, 0, b->stream>>>(
-        b->d_x, b->d_t, d_x0, S, (unsigned)b->ldn, (unsigned)b->n, 0.0, 1, 0);
+        b->d_x, b->d_t, b->d_x0, S, (unsigned)b->ldn, (unsigned)b->n, 0.0, 1, 0);
     RB_CUDA(cudaGetLastError());
     ++g_kernel_launches;
-    RB_CUDA(cudaStreamSynchronize(b->stream));  // h goes out of scope
-    RB_CUDA(cudaFreeAsync(d_x0, b->stream));
   } else {
     std::vector<int> h((size_t)S * b->ldn, 0);
     for (size_t n = 0; n < b->n; ++n)
       for (uint32_t s = 0; s < S; ++s) h[(size_t)s * b->ldn + n] = (int)x0[n * S + s];
     RB_CUDA(cudaMemcpyAsync(b->d_x, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-    RB_CUDA(cudaStreamSynchronize(b->stream));
   }
+  b->pend.active = false;  // new state: a call cut short earlier cannot be continued
   return REBOP_OK;
 }
 
@@ -244,12 +297,13 @@ static int upload_seeds(rebop_batch* b, const uint64_t* seeds, uint64_t seed_bas
   if (seeds) {
     if (!b->d_seeds) RB_CUDA(cudaMalloc(&b->d_seeds, b->ldn * sizeof(rb_u64)));
     RB_CUDA(cudaMemcpyAsync(b->d_seeds, seeds, b->n * sizeof(rb_u64), cudaMemcpyHostToDevice, b->stream));
-    RB_CUDA(cudaStreamSynchronize(b->stream));
+    RB_CUDA(cudaStreamSynchronize(b->stream));  // the caller's array may be page-locked: the copy must have read it before we return
     b->seed_mode = 1;
   } else {
     b->seed_base = seed_base;
     b->seed_mode = 2;
   }
+  b->pend.active = false;
   return REBOP_OK;
 }
 
@@ -263,9 +317,12 @@ extern "C" void rebop_batch_destroy(rebop_batch* b) {
   if (b->own_stream && b->own_stream != b->stream) cudaStreamSynchronize(b->own_stream);
   cudaFree(b->d_x); cudaFree(b->d_t); cudaFree(b->d_rng); cudaFree(b->d_seeds);
   cudaFree(b->d_out); cudaFree(b->d_counters); cudaFree(b->d_sums); cudaFree(b->d_gtab);
-  cudaFree(b->d_ev_counts); cudaFree(b->d_ev_offsets); cudaFree(b->d_ev_times); cudaFree(b->d_grid_t);
+  cudaFree(b->d_raw); cudaFree(b->d_stat32); cudaFree(b->d_progress); cudaFree(b->d_tables); cudaFree(b->d_x0);
+  if (b->h_counters) cudaFreeHost(b->h_counters);
+  cudaFree(b->d_ev_counts); cudaFree(b->d_ev_offsets); cudaFree(b->d_ev_times); cudaFree(b->d_ev_out); cudaFree(b->d_grid_t);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->ev2) cudaEventDestroy(b->ev2);
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   if (b->own_stream) cudaStreamDestroy(b->own_stream);
   delete b;
@@ -302,9 +359,13 @@ extern "C" int rebop_batch_create(const rebop_network* net, int device, size_t n
   b->stream = b->own_stream;
   RB_CREATE_CUDA(cudaEventCreate(&b->ev0));
   RB_CREATE_CUDA(cudaEventCreate(&b->ev1));
+  RB_CREATE_CUDA(cudaEventCreate(&b->ev2));
   RB_CREATE_CUDA(cudaMalloc(&b->d_x, S * b->ldn * sizeof(int)));
   RB_CREATE_CUDA(cudaMalloc(&b->d_t, b->ldn * sizeof(double)));
   RB_CREATE_CUDA(cudaMalloc(&b->d_rng, 4 * b->ldn * sizeof(rb_u64)));
+  RB_CREATE_CUDA(cudaMalloc(&b->d_x0, S * sizeof(int)));
+  RB_CREATE_CUDA(cudaMalloc(&b->d_progress, b->ldn * sizeof(rb_u32)));
+  RB_CREATE_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&b->h_counters), 4 * sizeof(rb_u64), cudaHostAllocDefault));
   RB_CREATE_CUDA(cudaMalloc(&b->d_counters, 4 * sizeof(rb_u64)));
   RB_CREATE_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
   RB_CREATE_CUDA(cudaMemsetAsync(b->d_rng, 0, 4 * b->ldn * sizeof(rb_u64), b->stream));
@@ -338,17 +399,19 @@ extern "C" int rebop_batch_set_rates(rebop_batch* b, const double* k, size_t n_r
     if (!b->net.rx[r].is_expr) b->net.rx[r].k = k[r];
   int st = rb_lower_tables(b->net, &b->tables);
   b->tables_ok = (st == REBOP_OK);
+  b->tables_uploaded = false;
   if (!b->tables_ok) b->tables_error = rebop_b200_last_error();
   return REBOP_OK;
 }
 extern "C" int rebop_batch_set_schedule(rebop_batch* b, int schedule) {
-  if (!b || schedule < 0 || schedule > 2) return rb_fail(REBOP_ERR_INVALID, "schedule must be 0 (auto), 1 (static) or 2 (dynamic)");
+  if (!b || schedule < 0 || schedule > 3)
+    return rb_fail(REBOP_ERR_INVALID, "schedule must be 0 (auto), 1 (static), 2 (dynamic, sparse samples) or 3 (dynamic, dense samples)");
   b->schedule = schedule;
   return REBOP_OK;
 }
 extern "C" int rebop_batch_get_schedule(const rebop_batch* b, int* schedule_used) {
   if (!b || !schedule_used) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
-  *schedule_used = b->dynamic_last ? 2 : 1;
+  *schedule_used = b->mode_last + 1;
   return REBOP_OK;
 }
 extern "C" int rebop_batch_set_max_iters(rebop_batch* b, uint32_t max_iters) {
@@ -361,11 +424,31 @@ extern "C" int rebop_batch_size(const rebop_batch* b, size_t* n_traj) {
   *n_traj = b->n;
   return REBOP_OK;
 }
+// Launches on a caller-owned stream (rebop_batch_set_stream) do not block the host: their counters and status arrive
+// in the page-locked mirror and are accounted for here, after the stream has drained.
+static int account_async(rebop_batch* b) {
+  if (!b->async_pending) return REBOP_OK;
+  b->async_pending = false;
+  b->events_last = b->h_counters[0];
+  b->lane_slots_last = b->h_counters[2];
+  b->events_total += b->h_counters[0];
+  const rb_u64 status = b->h_counters[1];
+  if (status & RB_STATUS_NARROW)
+    return rb_fail(REBOP_ERR_LIMIT, "a sample does not fit the batch's 16-bit sample type (rebop_batch_set_sample_dtype)");
+  if (status & RB_STATUS_ITER_CAP)
+    return rb_fail(REBOP_ERR_ITER_CAP, "a trajectory hit the per-launch iteration cap before reaching its target time");
+  return REBOP_OK;
+}
+
+static int sync_stream(rebop_batch* b) {
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  return account_async(b);
+}
+
 extern "C" int rebop_batch_synchronize(rebop_batch* b) {
   if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   RB_CUDA(cudaSetDevice(b->device));
-  RB_CUDA(cudaStreamSynchronize(b->stream));
-  return REBOP_OK;
+  return sync_stream(b);
 }
 
 extern "C" int rebop_batch_get_stream(const rebop_batch* b, void** stream) {
@@ -376,9 +459,9 @@ extern "C" int rebop_batch_get_stream(const rebop_batch* b, void** stream) {
 extern "C" int rebop_batch_set_stream(rebop_batch* b, void* stream) {
   if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   RB_CUDA(cudaSetDevice(b->device));
-  RB_CUDA(cudaStreamSynchronize(b->stream));  // hand over with nothing in flight on the old stream
+  int st = sync_stream(b);  // hand over with nothing in flight on the old stream
   b->stream = stream ? static_cast<cudaStream_t>(stream) : b->own_stream;
-  return REBOP_OK;
+  return st;
 }
 
 extern "C" int rebop_b200_host_alloc(size_t bytes, void** out) {
@@ -404,8 +487,7 @@ extern "C" int rebop_batch_get_time(rebop_batch* b, double* t) {
   if (!b || !t) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   RB_CUDA(cudaSetDevice(b->device));
   RB_CUDA(cudaMemcpyAsync(t, b->d_t, b->n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-  RB_CUDA(cudaStreamSynchronize(b->stream));
-  return REBOP_OK;
+  return sync_stream(b);
 }
 
 extern "C" int rebop_batch_set_time(rebop_batch* b, double t) {
@@ -415,6 +497,7 @@ extern "C" int rebop_batch_set_time(rebop_batch* b, double t) {
       b->d_x, b->d_t, nullptr, 0, (unsigned)b->ldn, (unsigned)b->n, t, 0, 1);
   RB_CUDA(cudaGetLastError());
   ++g_kernel_launches;
+  b->pend.active = false;
   return REBOP_OK;
 }
 
@@ -422,12 +505,18 @@ extern "C" int rebop_batch_get_species(rebop_batch* b, int64_t* species) {
   if (!b || !species) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   RB_CUDA(cudaSetDevice(b->device));
   const uint32_t S = b->net.n_species;
-  std::vector<int> h((size_t)S * b->ldn);
-  RB_CUDA(cudaMemcpyAsync(h.data(), b->d_x, h.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  RB_CUDA(cudaStreamSynchronize(b->stream));
-  for (size_t n = 0; n < b->n; ++n)
-    for (uint32_t s = 0; s < S; ++s) species[n * S + s] = h[(size_t)s * b->ldn + n];
-  return REBOP_OK;
+  if (S == 0) return REBOP_OK;
+  long long* d_rows = nullptr;  // [n][S] int64, transposed and widened on the device
+  const size_t total = b->n * S;
+  RB_CUDA(cudaMallocAsync(&d_rows, total * sizeof(long long), b->stream));
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)b->sm_count * 16);
+  rb_species_rows_kernel<<<blocks, 256, 0, b->stream>>>(b->d_x, d_rows, S, (unsigned)b->ldn, (unsigned)b->n);
+  ++g_kernel_launches;
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaMemcpyAsync(species, d_rows, total * sizeof(long long), cudaMemcpyDeviceToHost, b->stream);
+  cudaFreeAsync(d_rows, b->stream);
+  if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("rebop_batch_get_species: ") + cudaGetErrorString(err));
+  return sync_stream(b);
 }
 
 extern "C" int rebop_batch_set_species(rebop_batch* b, const int64_t* species, int per_trajectory) {
@@ -503,17 +592,19 @@ static int upload_gtab(rebop_batch* b, const uint32_t* save_idx, uint32_t n_save
   return REBOP_OK;
 }
 
-// Auto schedule.  The dynamic variant pays when trajectories are long compared with the samples they emit
-// (no lane idles behind the slowest trajectory of its warp, and its pass draws ahead and runs straight-line:
-// faster even when the whole ensemble is resident at once); the static schedule pays when samples are
-// dense (ring-staged, coalesced rows, no stream step-back per crossing).  The number of events is not known in advance; the total
-// propensity of the first trajectory's initial state times the horizon is a (low) estimate that orders
-// the workloads correctly: SIR 0.04 events per sample, Dimers 3, Vilar 5, Michaelis-Menten 15.
-static bool rb_auto_dynamic(const rebop_batch* b, double tmax, unsigned n_save, unsigned n_points) {
-  if (n_save == 0) return true;
+// Auto schedule.  Lanes claim trajectories in both automatic choices (no lane idles behind the slowest trajectory
+// of its warp, absorbed trajectories stop at once); what differs is when the uniform is drawn.  SPARSE draws both
+// random words ahead of the propensities and steps the stream back on a grid crossing: best when crossings are
+// rare.  DENSE draws the uniform once the event is known to fire: best when most passes of a warp contain a
+// crossing.  The number of events is not known in advance; the total propensity of the first trajectory's initial
+// state times the horizon is a (low) estimate that orders the workloads correctly: SIR 0.04 events per sample,
+// Dimers 3, Vilar 5, Michaelis-Menten 15.  The static schedule (ring-staged rows, thread n = trajectory n) is kept
+// for callers that ask for it.
+static int rb_auto_mode(const rebop_batch* b, double tmax, unsigned n_save, unsigned n_points) {
+  if (n_save == 0) return RB_MODE_SPARSE;
   double a0 = 0.0;
   for (const RbReaction& rx : b->net.rx) {
-    if (rx.is_expr) return true;
+    if (rx.is_expr) return RB_MODE_SPARSE;
     double a = rx.k;
     for (size_t j = 0; j < rx.term_idx.size(); ++j) {
       const double x = rx.term_idx[j] < b->x_first.size() ? (double)b->x_first[rx.term_idx[j]] : 0.0;
@@ -521,7 +612,7 @@ static bool rb_auto_dynamic(const rebop_batch* b, double tmax, unsigned n_save, 
     }
     if (a > 0.0) a0 += a;
   }
-  return a0 * tmax >= (double)n_save * n_points;
+  return a0 * tmax >= (double)n_save * n_points ? RB_MODE_SPARSE : RB_MODE_DENSE;
 }
 
 // Pending seeding (rebop_batch_create / rebop_batch_seed) is applied on the stream before the next launch.
@@ -543,6 +634,7 @@ static void fill_params(const rebop_batch* b, SsaRunParams* p) {
   p->events = b->d_counters;
   p->status = reinterpret_cast<rb_u32*>(b->d_counters + 1);
   p->work_next = reinterpret_cast<rb_u32*>(b->d_counters + 3);
+  p->progress = b->d_progress;
   p->n_traj = (rb_u32)b->n;
   p->ldn = (rb_u32)b->ldn;
   p->max_iters = b->max_iters;
@@ -551,6 +643,18 @@ static void fill_params(const rebop_batch* b, SsaRunParams* p) {
   p->one_m_eps = 1.0 - 0x1.0p-53;
   for (int l = 0; l < 4; ++l) p->byte_sel[l] = 1 << (8 * l);
   for (size_t r = 0; r < b->net.rx.size() && r < RB_MAX_K; ++r) p->k[r] = b->net.rx[r].k;
+  p->n_species = (int)b->net.n_species;
+  p->n_reactions = (int)b->net.rx.size();
+  p->arith = b->net.arith;
+}
+
+// The table-driven kernel reads its network from the batch's own device image (nothing process-global).
+static int upload_tables(rebop_batch* b) {
+  if (b->tables_uploaded) return REBOP_OK;
+  if (!b->d_tables) RB_CUDA(cudaMalloc(&b->d_tables, sizeof(RbTables)));
+  RB_CUDA(cudaMemcpyAsync(b->d_tables, &b->tables, sizeof(RbTables), cudaMemcpyHostToDevice, b->stream));
+  b->tables_uploaded = true;
+  return REBOP_OK;
 }
 
 // Build-time specialised, else NVRTC-specialised, else table-driven (use_jit = false).  `events` asks
@@ -589,8 +693,47 @@ static int pick_kernel(rebop_batch* b, bool events, RbJitKernel* jit, bool* use_
   return REBOP_OK;
 }
 
-static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_first, uint32_t step_last,
-                  int* d_out, uint32_t n_save, const uint32_t* save_idx, unsigned grid_points_total = 0) {
+template <class T>
+static int ensure_capacity(T** ptr, size_t* capacity, size_t need) {
+  if (need <= *capacity) return REBOP_OK;
+  if (*ptr) RB_CUDA(cudaFree(*ptr));
+  *ptr = nullptr;
+  *capacity = 0;
+  RB_CUDA(cudaMalloc(reinterpret_cast<void**>(ptr), need * sizeof(T)));
+  *capacity = need;
+  return REBOP_OK;
+}
+
+static bool is_async(const rebop_batch* b) { return b->stream != b->own_stream; }
+
+// Start of an API call that launches: per-call counters.  On a caller-owned stream the counters keep accumulating
+// until the caller synchronises (rebop_batch_synchronize reports them).
+static int begin_call(rebop_batch* b) {
+  if (!b->async_pending) RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
+  return REBOP_OK;
+}
+
+// End of an API call that launched: counters and status back to the host.  Blocks unless the stream is the caller's.
+static int end_call(rebop_batch* b, const char* what) {
+  RB_CUDA(cudaMemcpyAsync(b->h_counters, b->d_counters, 4 * sizeof(rb_u64), cudaMemcpyDeviceToHost, b->stream));
+  b->async_pending = true;
+  if (is_async(b)) return REBOP_OK;
+  RB_CUDA(cudaStreamSynchronize(b->stream));
+  b->async_pending = false;
+  b->events_last = b->h_counters[0];
+  b->lane_slots_last = b->h_counters[2];
+  b->events_total += b->h_counters[0];
+  if (b->h_counters[1] & RB_STATUS_NARROW)
+    return rb_fail(REBOP_ERR_LIMIT, "a sample does not fit the batch's 16-bit sample type (rebop_batch_set_sample_dtype)");
+  if (b->h_counters[1] & RB_STATUS_ITER_CAP) return rb_fail(REBOP_ERR_ITER_CAP, what);
+  return REBOP_OK;
+}
+
+// One launch of the ensemble loop over grid points step_first..step_last (inclusive) of a grid of nb_steps steps
+// (nb_steps = 0: the single target tmax), followed -- when samples are taken -- by the kernel that brings them into
+// the result layout at row `row_first` of d_out.  Everything is stream-ordered; nothing here blocks the host.
+static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_first, uint32_t step_last, bool sample,
+                  uint32_t n_save, const uint32_t* save_idx, bool resuming, unsigned grid_points_total = 0) {
   const uint32_t S = b->net.n_species;
   {
     int st = apply_seeding(b);
@@ -598,15 +741,18 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   }
   SsaRunParams p;
   fill_params(b, &p);
-  p.out = d_out;
   p.tmax = tmax;
   p.nb_steps = nb_steps;
   p.step_first = step_first;
   p.step_last = step_last;
-  p.n_save = d_out ? n_save : 0;
+  p.n_save = sample ? n_save : 0;
+  p.resuming = resuming ? 1u : 0u;
   const unsigned n_points = step_last - step_first + 1;
+  const size_t rows = (size_t)n_points * p.n_save;
+  const size_t row_first = (size_t)step_first * p.n_save;
 
-  RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
+  if (!resuming) RB_CUDA(cudaMemsetAsync(b->d_progress, 0, b->ldn * sizeof(rb_u32), b->stream));
+  RB_CUDA(cudaMemsetAsync(b->d_counters + 3, 0, sizeof(rb_u64), b->stream));  // work counter of this launch
 
   // grid times, exactly as the binding computes them: tmax * i as f64 / nb_steps as f64 (src/pyo3_gillespie.rs:201)
   std::vector<double> grid_t;
@@ -616,25 +762,21 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
       volatile double prod = tmax * (double)(step_first + i);  // volatile: one rounding per operation, no contraction
       grid_t[i] = prod / (double)nb_steps;
     }
-    if (n_points > b->grid_t_capacity) {
-      if (b->d_grid_t) RB_CUDA(cudaFree(b->d_grid_t));
-      b->d_grid_t = nullptr;
-      b->grid_t_capacity = 0;
-      RB_CUDA(cudaMalloc(&b->d_grid_t, n_points * sizeof(double)));
-      b->grid_t_capacity = n_points;
-    }
+    int st = ensure_capacity(&b->d_grid_t, &b->grid_t_capacity, (size_t)n_points);
+    if (st) return st;
     RB_CUDA(cudaMemcpyAsync(b->d_grid_t, grid_t.data(), n_points * sizeof(double), cudaMemcpyHostToDevice, b->stream));
     p.grid_t = b->d_grid_t;
   }
 
-  // --- schedule: dynamic when asked for, or (auto) when samples are sparse enough (rb_auto_dynamic)
+  // --- schedule
   int schedule = b->schedule;
   if (const char* env = std::getenv("REBOP_B200_SCHEDULE")) {
     if (!std::strcmp(env, "static")) schedule = 1;
-    if (!std::strcmp(env, "dynamic")) schedule = 2;
+    if (!std::strcmp(env, "dynamic") || !std::strcmp(env, "sparse")) schedule = 2;
+    if (!std::strcmp(env, "dense")) schedule = 3;
   }
-  const bool want_dynamic =
-      schedule == 2 || (schedule == 0 && rb_auto_dynamic(b, tmax, p.n_save, grid_points_total ? grid_points_total : n_points));
+  const int mode = schedule ? schedule - 1 : rb_auto_mode(b, tmax, p.n_save, grid_points_total ? grid_points_total : n_points);
+  const bool claim = mode != RB_MODE_STATIC;
 
   RbJitKernel jit;
   bool use_jit = false;
@@ -642,6 +784,24 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   {
     int st = pick_kernel(b, false, &jit, &use_jit, &jit_kind);
     if (st) return st;
+  }
+
+  // --- where the kernel puts its samples
+  int* static_rows = nullptr;  // static schedule: int32 [rows][ldn]
+  if (p.n_save) {
+    if (claim) {
+      int st = ensure_capacity(&b->d_raw, &b->raw_capacity, b->n * rows);
+      if (st) return st;
+      p.out = b->d_raw;
+    } else if (b->sample_bytes == 4) {
+      static_rows = static_cast<int*>(b->d_out) + row_first * b->ldn;
+      p.out = static_rows;
+    } else {
+      int st = ensure_capacity(&b->d_stat32, &b->stat32_capacity, rows * b->ldn);
+      if (st) return st;
+      static_rows = b->d_stat32;
+      p.out = static_rows;
+    }
   }
 
   RB_CUDA(cudaEventRecord(b->ev0, b->stream));
@@ -656,73 +816,128 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
       if (st) return st;
       p.gtab = b->d_gtab;
     }
-    p.ring_depth = want_dynamic ? 0u : choose_ring_depth(b, block, jit.net_words + jit.static_smem / 4u, p.n_save, n_points, ctas);
+    p.ring_depth = claim ? 0u : choose_ring_depth(b, block, jit.net_words + jit.static_smem / 4u, p.n_save, n_points, ctas);
     const size_t smem = RB_SSA_SMEM_BYTES(jit.net_words, block, p.ring_depth, p.n_save);
     if (smem + RB_STATIC_SMEM_BYTES + jit.static_smem > (size_t)b->max_smem_optin)
       return rb_fail(REBOP_ERR_LIMIT, "specialised kernel: species state does not fit in shared memory");
     unsigned grid = (unsigned)((b->n + block - 1) / block);
-    if (want_dynamic) {
+    if (claim) {
       int resident = 0;
-      int st = rb_jit_occupancy(jit, true, smem, &resident);
+      int st = rb_jit_occupancy(jit, mode, smem, &resident);
       if (st) return st;
       grid = std::min(grid, (unsigned)std::max(1, resident) * (unsigned)b->sm_count);
       p.dynamic = 1;
       p.n_launched = grid * block;
     }
-    int st = rb_jit_launch(jit, want_dynamic, p, grid, smem, b->stream);
+    int st = rb_jit_launch(jit, mode, p, grid, smem, b->stream);
     if (st) return st;
     b->kernel_used = jit_kind;
   } else {
     if (p.n_save > RB_TAB_MAX_SAVE) return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: more than 1024 saved species");
-    for (uint32_t j = 0; j < p.n_save; ++j) b->tables.save_idx[j] = (unsigned short)save_idx[j];
     {
       int st = upload_gtab(b, save_idx, p.n_save);
+      if (!st) st = upload_tables(b);
       if (st) return st;
       p.gtab = b->d_gtab;
+      p.tables = b->d_tables;
     }
     const unsigned block = RB_TABLE_BLOCK;
     const unsigned net_words = S * block;
-    p.ring_depth = want_dynamic ? 0u : choose_ring_depth(b, block, net_words, p.n_save, n_points, 8);
+    p.ring_depth = claim ? 0u : choose_ring_depth(b, block, net_words, p.n_save, n_points, 8);
     const size_t smem = RB_SSA_SMEM_BYTES(net_words, block, p.ring_depth, p.n_save);
     if (smem + RB_STATIC_SMEM_BYTES > (size_t)b->max_smem_optin)
       return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: species state and sample ring do not fit in shared memory");
     unsigned grid = (unsigned)((b->n + block - 1) / block);
-    if (want_dynamic) {
+    if (claim) {
       int resident = 0;
-      RB_CUDA(rb_table_occupancy(true, smem, &resident));
+      RB_CUDA(rb_table_occupancy(mode, smem, &resident));
       grid = std::min(grid, (unsigned)std::max(1, resident) * (unsigned)b->sm_count);
       p.dynamic = 1;
       p.n_launched = grid * block;
     }
-    RB_CUDA(rb_table_launch(&b->tables, want_dynamic, p, grid, smem, b->stream));
+    RB_CUDA(rb_table_launch(mode, p, grid, smem, b->stream));
     b->kernel_used = REBOP_KERNEL_TABLE;
   }
   RB_CUDA(cudaEventRecord(b->ev1, b->stream));
   ++g_kernel_launches;
+  b->mode_last = mode;
 
-  rb_u64 counters[4] = {0, 0, 0, 0};
-  RB_CUDA(cudaMemcpyAsync(counters, b->d_counters, sizeof counters, cudaMemcpyDeviceToHost, b->stream));
-  RB_CUDA(cudaStreamSynchronize(b->stream));
-  RB_CUDA(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
-  b->dynamic_last = p.dynamic != 0;
-  b->events_last = counters[0];
-  b->lane_slots_last = counters[2];
-  b->events_total += counters[0];
-  if (counters[1] & RB_STATUS_ITER_CAP)
-    return rb_fail(REBOP_ERR_ITER_CAP, "a trajectory hit the per-launch iteration cap before reaching its target time");
+  // --- samples into the result layout and sample type
+  if (p.n_save) {
+    char* dst = static_cast<char*>(b->d_out) + row_first * b->ldn * (size_t)b->sample_bytes;
+    if (claim) {
+      RbFinishParams q;
+      q.raw = b->d_raw;
+      q.progress = b->d_progress;
+      q.out = dst;
+      q.sums = b->d_sums + row_first;
+      q.sums_stride = b->out_rows;
+      q.status = p.status;
+      q.n = (rb_u32)b->n;
+      q.ldn = (rb_u32)b->ldn;
+      q.n_points = n_points;
+      q.n_save = p.n_save;
+      q.rows = (rb_u32)rows;
+      RB_CUDA(cudaMemsetAsync(b->d_sums + row_first, 0, rows * sizeof(rb_i64), b->stream));
+      RB_CUDA(cudaMemsetAsync(b->d_sums + b->out_rows + row_first, 0, rows * sizeof(rb_i64), b->stream));
+      static const bool bulk = [] {
+        const char* env = std::getenv("REBOP_B200_BULK_STORE");
+        return !(env && env[0] == '0');
+      }();
+      RB_CUDA(rb_samples_finish(q, b->sample_bytes, bulk, (unsigned)b->sm_count, b->stream));
+      ++g_kernel_launches;
+      b->sums_ready = true;
+    } else if (b->sample_bytes != 4) {
+      RB_CUDA(rb_rows_convert(static_rows, dst, rows * b->ldn, b->sample_bytes, p.status, (unsigned)b->sm_count, b->stream));
+      ++g_kernel_launches;
+    }
+    RB_CUDA(cudaEventRecord(b->ev2, b->stream));
+  }
   return REBOP_OK;
+}
+
+// Times of the last launch: ensemble loop (ev0..ev1) and sample finishing (ev1..ev2).  Needs the stream drained.
+static void read_times(rebop_batch* b, bool sampled, float* loop_ms, float* finish_ms) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) *loop_ms += ms;
+  if (sampled && cudaEventElapsedTime(&ms, b->ev1, b->ev2) == cudaSuccess) *finish_ms += ms;
 }
 
 extern "C" int rebop_batch_advance_until(rebop_batch* b, double tmax) {
   if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   RB_CUDA(cudaSetDevice(b->device));
-  return launch(b, tmax, 0, 0, 0, nullptr, 0, nullptr);
+  // a repeat of the call the watchdog cut short continues it: finished trajectories are left alone
+  const bool resuming = b->pend.active && b->pend.kind == 0 && b->pend.tmax == tmax;
+  b->pend.active = false;
+  int st = begin_call(b);
+  if (!st) st = launch(b, tmax, 0, 0, 0, false, 0, nullptr, resuming);
+  if (st) return st;
+  st = end_call(b, "a trajectory hit the per-launch iteration cap before reaching its target time (call again to continue)");
+  if (!is_async(b)) {
+    b->last_ms = b->last_finish_ms = 0.f;
+    read_times(b, false, &b->last_ms, &b->last_finish_ms);
+  }
+  if (st == REBOP_ERR_ITER_CAP) {
+    b->pend.active = true;
+    b->pend.kind = 0;
+    b->pend.tmax = tmax;
+  }
+  return st;
 }
 
-extern "C" int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
-                                    uint32_t n_save, int32_t* host_out) {
+static int copy_rows_to_host(rebop_batch* b, void* host, size_t host_ld, size_t row_first, size_t rows, cudaStream_t stream) {
+  const size_t sb = (size_t)b->sample_bytes;
+  RB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(host) + row_first * host_ld * sb, host_ld * sb,
+                            static_cast<const char*>(b->d_out) + row_first * b->ldn * sb, b->ldn * sb, b->n * sb, rows,
+                            cudaMemcpyDeviceToHost, stream));
+  return REBOP_OK;
+}
+
+static int run_grid_impl(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx, uint32_t n_save, void* host_out,
+                         size_t host_ld) {
   if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   if (nb_steps == 0) return rb_fail(REBOP_ERR_INVALID, "run_grid needs nb_steps >= 1 (nb_steps = 0 is the event-log mode)");
+  if (host_out && host_ld < b->n) return rb_fail(REBOP_ERR_INVALID, "ld must be at least the number of trajectories of the batch");
   RB_CUDA(cudaSetDevice(b->device));
   const uint32_t S = b->net.n_species;
   std::vector<uint32_t> all;
@@ -738,53 +953,183 @@ extern "C" int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_ste
       return rb_fail(REBOP_ERR_INVALID, "save_idx must be strictly increasing");
   }
   const size_t rows = (size_t)(nb_steps + 1) * n_save;
-  const size_t need = std::max<size_t>(1, rows * b->ldn);
-  if (need > b->out_capacity) {
-    if (b->d_out) RB_CUDA(cudaFree(b->d_out));
-    b->d_out = nullptr;
-    b->out_capacity = 0;
-    RB_CUDA(cudaMalloc(&b->d_out, need * sizeof(int)));
-    b->out_capacity = need;
+  if (rows > 0x7fffffffu) return rb_fail(REBOP_ERR_LIMIT, "more than 2^31 sample rows");
+  // a repeat of the call the watchdog cut short continues it from the segment and grid points reached
+  const bool resuming = b->pend.active && b->pend.kind == 1 && b->pend.tmax == tmax && b->pend.nb_steps == nb_steps &&
+                        b->pend.save == std::vector<uint32_t>(save_idx, save_idx + n_save);
+  const unsigned seg_first = resuming ? b->pend.segment : 0u;
+  b->pend.active = false;
+  {
+    int st = ensure_capacity(reinterpret_cast<char**>(&b->d_out), &b->out_capacity, std::max<size_t>(1, rows * b->ldn) * b->sample_bytes);
+    if (!st) st = ensure_capacity(&b->d_sums, &b->sums_capacity, std::max<size_t>(2, 2 * rows));
+    if (st) return st;
   }
   b->out_rows = (uint32_t)rows;
   b->out_n_save = n_save;
   b->out_nb_steps = nb_steps;
-  // With a host buffer and a result worth the trouble, the grid runs as a few segments of consecutive grid
-  // points: the rows of a finished segment travel to the host while the next segment is being simulated
-  // (a launch that ends at grid point k leaves every trajectory exactly where a single launch would have it
-  // at that point, so the result does not depend on the segmentation).
+  if (!resuming) b->sums_ready = false;
+  // The grid runs as a few segments of consecutive grid points when that pays: with a host buffer and a result
+  // worth the trouble, the rows of a finished segment travel to the host while the next segment is being simulated;
+  // and a very large result bounds the per-trajectory record buffer of the claiming schedules (a launch that ends
+  // at grid point k leaves every trajectory exactly where a single launch would have it at that point, so the
+  // result does not depend on the segmentation).
   const size_t bytes = rows * b->n * sizeof(int);
   unsigned segments = 1;
   if (host_out && n_save && bytes >= ((size_t)256 << 20) && nb_steps + 1 >= 8) segments = 4;
-  if (segments == 1) {
-    int st = launch(b, tmax, nb_steps, 0, nb_steps, n_save ? b->d_out : nullptr, n_save, save_idx);
-    if (st) return st;
-    if (host_out) return rebop_batch_samples_host_i32(b, host_out);
-    return REBOP_OK;
-  }
-  if (!b->copy_stream) RB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
-  uint64_t events = 0, lane_slots = 0;
-  float ms = 0.f;
+  while (n_save && bytes / segments > ((size_t)16 << 30) && segments * 2 <= nb_steps + 1) segments *= 2;
+  const bool overlap = host_out && segments > 1 && !is_async(b);
+  if (overlap && !b->copy_stream) RB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+  uint64_t events = resuming ? b->pend.events : 0, lane_slots = resuming ? b->pend.lane_slots : 0;
+  float ms = resuming ? b->pend.ms : 0.f, finish_ms = 0.f;
   int st = REBOP_OK;
-  for (unsigned sgm = 0; sgm < segments && st == REBOP_OK; ++sgm) {
+  unsigned sgm = seg_first;
+  for (; sgm < segments && st == REBOP_OK; ++sgm) {
     const uint32_t first = (uint32_t)((uint64_t)(nb_steps + 1) * sgm / segments);
     const uint32_t last = (uint32_t)((uint64_t)(nb_steps + 1) * (sgm + 1) / segments) - 1;
-    st = launch(b, tmax, nb_steps, first, last, b->d_out + (size_t)first * n_save * b->ldn, n_save, save_idx, nb_steps + 1);
-    events += b->events_last;
-    lane_slots += b->lane_slots_last;
-    ms += b->last_ms;
-    if (st == REBOP_OK) {
-      cudaError_t err = cudaMemcpy2DAsync(host_out + (size_t)first * n_save * b->n, b->n * sizeof(int),
-                                          b->d_out + (size_t)first * n_save * b->ldn, b->ldn * sizeof(int), b->n * sizeof(int),
-                                          (size_t)(last - first + 1) * n_save, cudaMemcpyDeviceToHost, b->copy_stream);
-      if (err != cudaSuccess) st = rb_fail(REBOP_ERR_CUDA, std::string("cudaMemcpy2DAsync: ") + cudaGetErrorString(err));
+    st = begin_call(b);
+    if (!st) st = launch(b, tmax, nb_steps, first, last, n_save != 0, n_save, save_idx, resuming && sgm == seg_first, nb_steps + 1);
+    if (st) break;
+    if (host_out && n_save && is_async(b)) st = copy_rows_to_host(b, host_out, host_ld, (size_t)first * n_save, (size_t)(last - first + 1) * n_save, b->stream);
+    if (st) break;
+    st = end_call(b, "a trajectory hit the per-launch iteration cap before reaching its last grid point (call again to continue)");
+    if (!is_async(b)) {
+      events += b->events_last;
+      lane_slots += b->lane_slots_last;
+      read_times(b, n_save != 0, &ms, &finish_ms);
     }
+    if (st == REBOP_OK && host_out && n_save && !is_async(b))
+      st = copy_rows_to_host(b, host_out, host_ld, (size_t)first * n_save, (size_t)(last - first + 1) * n_save,
+                             overlap ? b->copy_stream : b->stream);
   }
-  cudaError_t err = cudaStreamSynchronize(b->copy_stream);
-  if (st == REBOP_OK && err != cudaSuccess) st = rb_fail(REBOP_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(err));
-  b->events_last = events;
-  b->lane_slots_last = lane_slots;
-  b->last_ms = ms;
+  if (!is_async(b)) {
+    cudaError_t err = cudaStreamSynchronize(overlap ? b->copy_stream : b->stream);
+    if (st == REBOP_OK && err != cudaSuccess) st = rb_fail(REBOP_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(err));
+    b->events_last = events;
+    b->lane_slots_last = lane_slots;
+    b->last_ms = ms;
+    b->last_finish_ms = finish_ms;
+  }
+  if (st == REBOP_ERR_ITER_CAP) {
+    b->pend.active = true;
+    b->pend.kind = 1;
+    b->pend.tmax = tmax;
+    b->pend.nb_steps = nb_steps;
+    b->pend.n_save = n_save;
+    b->pend.save.assign(save_idx, save_idx + n_save);
+    b->pend.segment = sgm;
+    b->pend.events = events;
+    b->pend.lane_slots = lane_slots;
+    b->pend.ms = ms;
+  }
+  return st;
+}
+
+extern "C" int rebop_batch_run_grid(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
+                                    uint32_t n_save, int32_t* host_out) {
+  if (b && host_out && b->sample_bytes != 4)
+    return rb_fail(REBOP_ERR_INVALID, "rebop_batch_run_grid writes int32 samples: use rebop_batch_run_grid_typed with this batch's sample type");
+  return run_grid_impl(b, tmax, nb_steps, save_idx, n_save, host_out, b ? b->n : 0);
+}
+
+extern "C" int rebop_batch_run_grid_typed(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
+                                          uint32_t n_save, void* host_out) {
+  return run_grid_impl(b, tmax, nb_steps, save_idx, n_save, host_out, b ? b->n : 0);
+}
+
+extern "C" int rebop_batch_run_grid_strided(rebop_batch* b, double tmax, uint32_t nb_steps, const uint32_t* save_idx,
+                                            uint32_t n_save, void* host_out, size_t ld) {
+  return run_grid_impl(b, tmax, nb_steps, save_idx, n_save, host_out, ld);
+}
+
+extern "C" int rebop_batch_set_sample_dtype(rebop_batch* b, int sample_bytes) {
+  if (!b || (sample_bytes != 2 && sample_bytes != 4 && sample_bytes != 8))
+    return rb_fail(REBOP_ERR_INVALID, "sample type must be REBOP_SAMPLES_I16, _I32 or _I64");
+  b->sample_bytes = sample_bytes;
+  b->out_rows = 0;  // samples of an earlier run are in the old type
+  b->pend.active = false;
+  return REBOP_OK;
+}
+extern "C" int rebop_batch_get_sample_dtype(const rebop_batch* b, int* sample_bytes) {
+  if (!b || !sample_bytes) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  *sample_bytes = b->sample_bytes;
+  return REBOP_OK;
+}
+
+// Launch set-up shared by the event-log entry points (kernels <name>_evc / <name>_evw).
+struct EventsLaunch {
+  SsaRunParams p;
+  RbJitKernel jit;
+  bool use_jit = false;
+  int jit_kind = REBOP_KERNEL_NVRTC;
+  unsigned block = RB_TABLE_BLOCK, grid = 1;
+  size_t smem = 0;
+};
+
+static int events_setup(rebop_batch* b, const uint32_t* save_idx, uint32_t n_save, EventsLaunch* e) {
+  const uint32_t S = b->net.n_species;
+  int st = pick_kernel(b, true, &e->jit, &e->use_jit, &e->jit_kind);
+  if (!st) st = apply_seeding(b);
+  if (st) return st;
+  SsaRunParams& p = e->p;
+  fill_params(b, &p);
+  p.n_save = n_save;
+  if (e->use_jit) {
+    for (uint32_t j = 0; j < n_save && save_idx[j] < 128; ++j) p.save_mask[save_idx[j] >> 6] |= 1ull << (save_idx[j] & 63u);
+    e->block = e->jit.block;
+    e->smem = RB_SSA_SMEM_BYTES(e->jit.net_words, e->block, 0, 0);
+  } else {
+    if (n_save > RB_TAB_MAX_SAVE) return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: more than 1024 saved species");
+    e->smem = RB_SSA_SMEM_BYTES(S * e->block, e->block, 0, 0);
+    if (e->smem + RB_STATIC_SMEM_BYTES > (size_t)b->max_smem_optin)
+      return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: species state does not fit in shared memory");
+    st = upload_tables(b);
+    if (st) return st;
+    p.tables = b->d_tables;
+  }
+  if (!e->use_jit || e->jit.large) {
+    st = upload_gtab(b, save_idx, n_save);
+    if (st) return st;
+    p.gtab = b->d_gtab;
+  }
+  e->grid = (unsigned)((b->n + e->block - 1) / e->block);
+  return REBOP_OK;
+}
+
+static int events_pass(rebop_batch* b, const EventsLaunch& e, bool write) {
+  if (e.use_jit) {
+    int rc = rb_jit_launch_entry(write ? e.jit.kernel_evw : e.jit.kernel_evc, e.block, e.p, e.grid, e.smem, b->stream);
+    if (rc) return rc;
+  } else {
+    RB_CUDA(rb_table_launch_events(write, e.p, e.grid, e.smem, b->stream));
+  }
+  ++g_kernel_launches;
+  return REBOP_OK;
+}
+
+// Gillespie::advance_one_reaction (src/gillespie.rs:270-297) on every trajectory: exactly one pass of the direct
+// method whatever the time -- propensities; an absorbing state sets t = +inf; otherwise t += Exp1 / total, uniform,
+// choice, update.  One launch of the event-log kernel limited to a single row, nothing logged.
+extern "C" int rebop_batch_advance_one_reaction(rebop_batch* b) {
+  if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  RB_CUDA(cudaSetDevice(b->device));
+  b->pend.active = false;
+  EventsLaunch e;
+  int st = events_setup(b, nullptr, 0, &e);
+  if (st) return st;
+  e.p.ev_single = 1;
+  st = begin_call(b);
+  if (st) return st;
+  RB_CUDA(cudaEventRecord(b->ev0, b->stream));
+  st = events_pass(b, e, true);
+  if (st) return st;
+  RB_CUDA(cudaEventRecord(b->ev1, b->stream));
+  b->kernel_used = e.use_jit ? e.jit_kind : REBOP_KERNEL_TABLE;
+  st = end_call(b, "iteration cap");
+  if (!is_async(b)) {
+    b->last_ms = b->last_finish_ms = 0.f;
+    read_times(b, false, &b->last_ms, &b->last_finish_ms);
+    b->lane_slots_last = 0;
+  }
   return st;
 }
 
@@ -805,55 +1150,22 @@ extern "C" int rebop_batch_run_events(rebop_batch* b, double tmax, const uint32_
     if (save_idx[j] >= S) return rb_fail(REBOP_ERR_OUT_OF_RANGE, "save_idx refers to a species index out of range");
     if (j > 0 && save_idx[j] <= save_idx[j - 1]) return rb_fail(REBOP_ERR_INVALID, "save_idx must be strictly increasing");
   }
-  RbJitKernel jit;
-  bool use_jit = false;
-  int jit_kind = REBOP_KERNEL_NVRTC;
-  int st = pick_kernel(b, true, &jit, &use_jit, &jit_kind);
+  b->pend.active = false;
+  int st = sync_stream(b);  // this entry point blocks (the log's size is data): earlier asynchronous work is accounted first
   if (st) return st;
-
-  st = apply_seeding(b);
+  EventsLaunch e;
+  st = events_setup(b, save_idx, n_save, &e);
   if (st) return st;
-  SsaRunParams p;
-  fill_params(b, &p);
+  SsaRunParams& p = e.p;
   p.tmax = tmax;
-  p.n_save = n_save;
-  unsigned block = RB_TABLE_BLOCK;
-  size_t smem = 0;
-  if (use_jit) {
-    for (uint32_t j = 0; j < n_save && save_idx[j] < 128; ++j) p.save_mask[save_idx[j] >> 6] |= 1ull << (save_idx[j] & 63u);
-    block = jit.block;
-    smem = RB_SSA_SMEM_BYTES(jit.net_words, block, 0, 0);
-  } else {
-    if (n_save > RB_TAB_MAX_SAVE) return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: more than 1024 saved species");
-    for (uint32_t j = 0; j < n_save; ++j) b->tables.save_idx[j] = (unsigned short)save_idx[j];
-    smem = RB_SSA_SMEM_BYTES(S * block, block, 0, 0);
-    if (smem + RB_STATIC_SMEM_BYTES > (size_t)b->max_smem_optin)
-      return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: species state does not fit in shared memory");
-  }
-  if (!use_jit || jit.large) {
-    st = upload_gtab(b, save_idx, n_save);
-    if (st) return st;
-    p.gtab = b->d_gtab;
-  }
-  const unsigned grid = (unsigned)((b->n + block - 1) / block);
   if (!b->d_ev_counts) RB_CUDA(cudaMalloc(&b->d_ev_counts, b->ldn * sizeof(rb_u32)));
   if (!b->d_ev_offsets) RB_CUDA(cudaMalloc(&b->d_ev_offsets, b->ldn * sizeof(rb_u64)));
-  auto run_pass = [&](bool write) -> int {
-    RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
-    if (use_jit) {
-      int rc = rb_jit_launch_entry(write ? jit.kernel_evw : jit.kernel_evc, block, p, grid, smem, b->stream);
-      if (rc) return rc;
-    } else {
-      RB_CUDA(rb_table_launch_events(&b->tables, write, p, grid, smem, b->stream));
-    }
-    ++g_kernel_launches;
-    return REBOP_OK;
-  };
 
   // pass 1: rows per trajectory
   p.ev_counts = b->d_ev_counts;
+  RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
   RB_CUDA(cudaEventRecord(b->ev0, b->stream));
-  st = run_pass(false);
+  st = events_pass(b, e, false);
   if (st) return st;
   std::vector<rb_u32> counts(b->n);
   rb_u64 counters[4] = {0, 0, 0, 0};
@@ -869,39 +1181,30 @@ extern "C" int rebop_batch_run_events(rebop_batch* b, double tmax, const uint32_
   size_t free_b = 0, total_b = 0;
   RB_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const size_t need_out = std::max<size_t>(1, (size_t)total * n_save);
-  const size_t extra = (need_out > b->out_capacity ? need_out * sizeof(int) : 0) +
+  const size_t extra = (need_out > b->ev_out_capacity ? need_out * sizeof(int) : 0) +
                        (total > b->ev_times_capacity ? (size_t)total * sizeof(double) : 0);
-  if (extra > free_b + b->out_capacity * sizeof(int) + b->ev_times_capacity * sizeof(double))
+  if (extra > free_b + b->ev_out_capacity * sizeof(int) + b->ev_times_capacity * sizeof(double))
     return rb_fail(REBOP_ERR_LIMIT, "event log does not fit in device memory: split the ensemble or save fewer species");
-  if (need_out > b->out_capacity) {
-    if (b->d_out) RB_CUDA(cudaFree(b->d_out));
-    b->d_out = nullptr;
-    b->out_capacity = 0;
-    RB_CUDA(cudaMalloc(&b->d_out, need_out * sizeof(int)));
-    b->out_capacity = need_out;
-  }
-  if (total > b->ev_times_capacity) {
-    if (b->d_ev_times) RB_CUDA(cudaFree(b->d_ev_times));
-    b->d_ev_times = nullptr;
-    b->ev_times_capacity = 0;
-    RB_CUDA(cudaMalloc(&b->d_ev_times, std::max<size_t>(1, total) * sizeof(double)));
-    b->ev_times_capacity = total;
-  }
+  st = ensure_capacity(&b->d_ev_out, &b->ev_out_capacity, need_out);
+  if (!st) st = ensure_capacity(&b->d_ev_times, &b->ev_times_capacity, std::max<size_t>(1, total));
+  if (st) return st;
   RB_CUDA(cudaMemcpyAsync(b->d_ev_offsets, b->ev_offsets.data(), b->n * sizeof(rb_u64), cudaMemcpyHostToDevice, b->stream));
 
   // pass 2: the same trajectories again, rows written at their offsets, final state written back
   p.ev_offsets = b->d_ev_offsets;
   p.ev_times = b->d_ev_times;
   p.ev_total = total;
-  p.out = n_save ? b->d_out : nullptr;
-  st = run_pass(true);
+  p.out = n_save ? b->d_ev_out : nullptr;
+  RB_CUDA(cudaMemsetAsync(b->d_counters, 0, 4 * sizeof(rb_u64), b->stream));
+  st = events_pass(b, e, true);
   if (st) return st;
   RB_CUDA(cudaEventRecord(b->ev1, b->stream));
   RB_CUDA(cudaMemcpyAsync(counters, b->d_counters, sizeof counters, cudaMemcpyDeviceToHost, b->stream));
   RB_CUDA(cudaStreamSynchronize(b->stream));
   RB_CUDA(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
-  b->kernel_used = use_jit ? jit_kind : REBOP_KERNEL_TABLE;
-  b->dynamic_last = false;
+  b->last_finish_ms = 0.f;
+  b->kernel_used = e.use_jit ? e.jit_kind : REBOP_KERNEL_TABLE;
+  b->mode_last = RB_MODE_STATIC;
   b->events_last = counters[0];
   b->events_total += counters[0];
   b->lane_slots_last = 0;
@@ -926,13 +1229,12 @@ extern "C" int rebop_batch_events_log_host(rebop_batch* b, uint64_t* offsets, do
   if (offsets) std::memcpy(offsets, b->ev_offsets.data(), b->ev_offsets.size() * sizeof(uint64_t));
   if (times && total) RB_CUDA(cudaMemcpyAsync(times, b->d_ev_times, total * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
   if (samples && total && b->ev_n_save)
-    RB_CUDA(cudaMemcpyAsync(samples, b->d_out, (size_t)total * b->ev_n_save * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    RB_CUDA(cudaMemcpyAsync(samples, b->d_ev_out, (size_t)total * b->ev_n_save * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   RB_CUDA(cudaStreamSynchronize(b->stream));
   return REBOP_OK;
 }
 
-extern "C" int rebop_batch_samples_device(const rebop_batch* b, const int32_t** dev_ptr, size_t* ld,
-                                          uint32_t* n_rows) {
+extern "C" int rebop_batch_samples_device(const rebop_batch* b, const void** dev_ptr, size_t* ld, uint32_t* n_rows) {
   if (!b) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   if (dev_ptr) *dev_ptr = b->d_out;
   if (ld) *ld = b->ldn;
@@ -940,35 +1242,65 @@ extern "C" int rebop_batch_samples_device(const rebop_batch* b, const int32_t** 
   return REBOP_OK;
 }
 
-extern "C" int rebop_batch_samples_host_i32(rebop_batch* b, int32_t* out) {
-  if (!b || !out) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
-  if (b->out_rows == 0) return REBOP_OK;
-  RB_CUDA(cudaSetDevice(b->device));
-  RB_CUDA(cudaMemcpy2DAsync(out, b->n * sizeof(int), b->d_out, b->ldn * sizeof(int), b->n * sizeof(int),
-                            b->out_rows, cudaMemcpyDeviceToHost, b->stream));
-  RB_CUDA(cudaStreamSynchronize(b->stream));
-  return REBOP_OK;
-}
-
-extern "C" int rebop_batch_samples_host_i32_strided(rebop_batch* b, int32_t* out, size_t ld) {
+// Samples in the batch's own sample type: row r goes to out[r * ld .. r * ld + n_traj).
+static int samples_host_native(rebop_batch* b, void* out, size_t ld) {
   if (!b || !out) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   if (ld < b->n) return rb_fail(REBOP_ERR_INVALID, "ld must be at least the number of trajectories of the batch");
   if (b->out_rows == 0) return REBOP_OK;
   RB_CUDA(cudaSetDevice(b->device));
-  RB_CUDA(cudaMemcpy2DAsync(out, ld * sizeof(int), b->d_out, b->ldn * sizeof(int), b->n * sizeof(int),
-                            b->out_rows, cudaMemcpyDeviceToHost, b->stream));
-  RB_CUDA(cudaStreamSynchronize(b->stream));
-  return REBOP_OK;
+  int st = copy_rows_to_host(b, out, ld, 0, b->out_rows, b->stream);
+  if (st) return st;
+  return sync_stream(b);
 }
+
+template <typename In, typename Out>
+static int retype_chunks(rebop_batch* b, Out* out) {
+  // a chunk of rows at a time through a device staging buffer of at most 256 MB
+  const size_t rows_per_chunk = std::max<size_t>(1, ((size_t)256 << 20) / (b->n * sizeof(Out)));
+  Out* d_stage = nullptr;
+  const size_t chunk_rows = std::min<size_t>(rows_per_chunk, b->out_rows);
+  RB_CUDA(cudaMalloc(&d_stage, chunk_rows * b->n * sizeof(Out)));
+  cudaError_t err = cudaSuccess;
+  for (size_t r0 = 0; r0 < b->out_rows && err == cudaSuccess; r0 += chunk_rows) {
+    const unsigned rows = (unsigned)std::min<size_t>(chunk_rows, b->out_rows - r0);
+    const unsigned blocks = (unsigned)std::min<size_t>(((size_t)rows * b->n + 255) / 256, (size_t)b->sm_count * 16);
+    rb_rows_retype_kernel<In, Out><<<blocks, 256, 0, b->stream>>>(static_cast<const In*>(b->d_out) + r0 * b->ldn, d_stage, (unsigned)b->n,
+                                                                 (unsigned)b->ldn, rows);
+    ++g_kernel_launches;
+    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpyAsync(out + r0 * b->n, d_stage, (size_t)rows * b->n * sizeof(Out), cudaMemcpyDeviceToHost, b->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(b->stream);  // the staging buffer is reused by the next chunk
+  }
+  cudaFree(d_stage);
+  if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("sample conversion: ") + cudaGetErrorString(err));
+  return account_async(b);
+}
+
+extern "C" int rebop_batch_samples_host(rebop_batch* b, void* out) { return samples_host_native(b, out, b ? b->n : 0); }
+
+extern "C" int rebop_batch_samples_host_i32(rebop_batch* b, int32_t* out) {
+  if (!b || !out) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  if (b->out_rows == 0) return REBOP_OK;
+  if (b->sample_bytes == 4) return samples_host_native(b, out, b->n);
+  RB_CUDA(cudaSetDevice(b->device));
+  if (b->sample_bytes == 2) return retype_chunks<short, int32_t>(b, out);
+  return retype_chunks<long long, int32_t>(b, out);
+}
+
+extern "C" int rebop_batch_samples_host_i32_strided(rebop_batch* b, int32_t* out, size_t ld) {
+  if (b && b->sample_bytes != 4) return rb_fail(REBOP_ERR_INVALID, "the batch's sample type is not int32: use rebop_batch_samples_host_strided");
+  return samples_host_native(b, out, ld);
+}
+
+extern "C" int rebop_batch_samples_host_strided(rebop_batch* b, void* out, size_t ld) { return samples_host_native(b, out, ld); }
 
 extern "C" int rebop_batch_samples_host_i64(rebop_batch* b, int64_t* out) {
   if (!b || !out) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
-  const size_t count = (size_t)b->out_rows * b->n;
-  std::vector<int32_t> tmp(count);
-  int st = rebop_batch_samples_host_i32(b, tmp.data());
-  if (st) return st;
-  for (size_t i = 0; i < count; ++i) out[i] = tmp[i];
-  return REBOP_OK;
+  if (b->out_rows == 0) return REBOP_OK;
+  if (b->sample_bytes == 8) return samples_host_native(b, out, b->n);
+  RB_CUDA(cudaSetDevice(b->device));
+  if (b->sample_bytes == 2) return retype_chunks<short, long long>(b, reinterpret_cast<long long*>(out));
+  return retype_chunks<int, long long>(b, reinterpret_cast<long long*>(out));
 }
 
 extern "C" int rebop_batch_sample_sums_device(rebop_batch* b, const int64_t** dev_ptr, uint32_t* n_rows) {
@@ -976,20 +1308,22 @@ extern "C" int rebop_batch_sample_sums_device(rebop_batch* b, const int64_t** de
   RB_CUDA(cudaSetDevice(b->device));
   const uint32_t rows = b->out_rows;
   if (rows == 0) return rb_fail(REBOP_ERR_INVALID, "no samples: call run_grid first");
-  if (2u * rows > b->sums_capacity) {
-    if (b->d_sums) RB_CUDA(cudaFree(b->d_sums));
-    b->d_sums = nullptr;
-    RB_CUDA(cudaMalloc(&b->d_sums, 2 * (size_t)rows * sizeof(rb_i64)));
-    b->sums_capacity = 2u * rows;
+  if (!b->sums_ready) {  // static schedule: the claiming schedules leave the sums behind with the samples
+    RB_CUDA(cudaMemsetAsync(b->d_sums, 0, 2 * (size_t)rows * sizeof(rb_i64), b->stream));
+    // enough CTAs per row to fill the machine, each thread moving 16 bytes per load
+    const unsigned per_row = (unsigned)std::max<size_t>(1, std::min<size_t>((b->n / 4 + 255) / 256,
+                                                          std::max<size_t>(1, (size_t)b->sm_count * 8 / rows + 1)));
+    dim3 grid(rows, per_row);
+    if (b->sample_bytes == 2)
+      rb_row_sums_kernel<short><<<grid, 256, 0, b->stream>>>(static_cast<const short*>(b->d_out), (unsigned)b->n, (unsigned)b->ldn, b->d_sums, rows);
+    else if (b->sample_bytes == 4)
+      rb_row_sums_kernel<int><<<grid, 256, 0, b->stream>>>(static_cast<const int*>(b->d_out), (unsigned)b->n, (unsigned)b->ldn, b->d_sums, rows);
+    else
+      rb_row_sums_kernel<long long><<<grid, 256, 0, b->stream>>>(static_cast<const long long*>(b->d_out), (unsigned)b->n, (unsigned)b->ldn, b->d_sums, rows);
+    RB_CUDA(cudaGetLastError());
+    ++g_kernel_launches;
+    b->sums_ready = true;
   }
-  RB_CUDA(cudaMemsetAsync(b->d_sums, 0, 2 * (size_t)rows * sizeof(rb_i64), b->stream));
-  // enough CTAs per row to fill the machine, each thread moving 16 bytes per load
-  const unsigned per_row = (unsigned)std::max<size_t>(1, std::min<size_t>((b->n / 4 + 255) / 256,
-                                                        std::max<size_t>(1, (size_t)b->sm_count * 8 / rows + 1)));
-  dim3 grid(per_row, rows);
-  rb_row_sums_kernel<<<grid, 256, 0, b->stream>>>(b->d_out, (unsigned)b->n, (unsigned)b->ldn, b->d_sums, rows);
-  RB_CUDA(cudaGetLastError());
-  ++g_kernel_launches;
   if (dev_ptr) *dev_ptr = reinterpret_cast<const int64_t*>(b->d_sums);
   if (n_rows) *n_rows = rows;
   return REBOP_OK;
@@ -1003,8 +1337,7 @@ extern "C" int rebop_batch_sample_sums(rebop_batch* b, int64_t* sum, uint64_t* s
   if (st) return st;
   RB_CUDA(cudaMemcpyAsync(sum, d, rows * sizeof(int64_t), cudaMemcpyDeviceToHost, b->stream));
   RB_CUDA(cudaMemcpyAsync(sumsq, d + rows, rows * sizeof(int64_t), cudaMemcpyDeviceToHost, b->stream));
-  RB_CUDA(cudaStreamSynchronize(b->stream));
-  return REBOP_OK;
+  return sync_stream(b);
 }
 
 extern "C" int rebop_batch_events(rebop_batch* b, uint64_t* total, uint64_t* last_launch) {
@@ -1023,6 +1356,12 @@ extern "C" int rebop_batch_lane_slots(rebop_batch* b, uint64_t* last_launch) {
 extern "C" int rebop_batch_last_kernel_ms(rebop_batch* b, float* ms) {
   if (!b || !ms) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
   *ms = b->last_ms;
+  return REBOP_OK;
+}
+
+extern "C" int rebop_batch_last_finish_ms(rebop_batch* b, float* ms) {
+  if (!b || !ms) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  *ms = b->last_finish_ms;
   return REBOP_OK;
 }
 

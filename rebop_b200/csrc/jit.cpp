@@ -116,8 +116,7 @@ int rb_prebuilt_get(const rebop_network& net, RbJitKernel* out) {
   if (!rb_codegen_supported(net, &why)) return rb_fail(REBOP_ERR_LIMIT, "network cannot be specialised: " + why);
   const RbPrebuilt* e = rb_find_prebuilt(rb_codegen_source(net, "rb_ssa_jit", nullptr));
   if (!e) return rb_fail(REBOP_ERR_INVALID, "no build-time kernel was generated for this network (see rebop_b200/systems)");
-  out->kernel = const_cast<void*>(e->kernel);
-  out->kernel_dyn = const_cast<void*>(e->kernel_dyn);
+  for (int m = 0; m < 3; ++m) out->grid_kernel[m] = const_cast<void*>(e->grid_kernel[m]);
   out->kernel_evc = const_cast<void*>(e->kernel_evc);
   out->kernel_evw = const_cast<void*>(e->kernel_evw);
   out->block = e->block;
@@ -201,12 +200,13 @@ int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out) {
   CacheEntry e;
   cudaError_t err = cudaLibraryLoadData(&e.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(err));
-  cudaKernel_t kernel = nullptr, kernel_dyn = nullptr;
-  err = cudaLibraryGetKernel(&kernel, e.lib, "rb_ssa_jit");
-  if (err == cudaSuccess) err = cudaLibraryGetKernel(&kernel_dyn, e.lib, "rb_ssa_jit_dyn");
+  const char* const names[3] = {"rb_ssa_jit", "rb_ssa_jit_dyn", "rb_ssa_jit_dns"};
+  for (int m = 0; m < 3 && err == cudaSuccess; ++m) {
+    cudaKernel_t kernel = nullptr;
+    err = cudaLibraryGetKernel(&kernel, e.lib, names[m]);
+    e.k.grid_kernel[m] = kernel;
+  }
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(err));
-  e.k.kernel = kernel;
-  e.k.kernel_dyn = kernel_dyn;
   e.k.block = info.block;
   e.k.net_words = info.net_words;
   e.k.static_smem = info.static_smem;
@@ -247,8 +247,22 @@ int rb_jit_get_events(const rebop_network& net, int device, RbJitKernel* out) {
   return REBOP_OK;
 }
 
+cudaError_t rb_raise_smem_limit(const void* kernel, size_t smem_bytes) {
+  static std::mutex mutex;
+  static std::map<std::pair<int, const void*>, size_t> limit;
+  int device = 0;
+  cudaError_t err = cudaGetDevice(&device);
+  if (err != cudaSuccess) return err;
+  std::lock_guard<std::mutex> lock(mutex);
+  size_t& cur = limit[std::make_pair(device, kernel)];
+  if (smem_bytes <= cur) return cudaSuccess;
+  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (err == cudaSuccess) cur = smem_bytes;
+  return err;
+}
+
 int rb_jit_launch_entry(void* kernel, unsigned block, const SsaRunParams& p, unsigned grid, size_t smem_bytes, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  cudaError_t err = rb_raise_smem_limit(kernel, smem_bytes);
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
   void* args[] = {const_cast<SsaRunParams*>(&p)};
   err = cudaLaunchKernel(kernel, dim3(grid), dim3(block), args, smem_bytes, stream);
@@ -279,19 +293,19 @@ extern "C" int rebop_network_jit_cubin(const rebop_network* net, char* buf, size
   return copy_out(cubin.data(), cubin.size(), buf, cap, needed);
 }
 
-int rb_jit_occupancy(const RbJitKernel& k, bool dynamic, size_t smem_bytes, int* ctas_per_sm) {
-  void* kernel = dynamic ? k.kernel_dyn : k.kernel;
-  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+int rb_jit_occupancy(const RbJitKernel& k, int mode, size_t smem_bytes, int* ctas_per_sm) {
+  void* kernel = k.grid_kernel[mode];
+  cudaError_t err = rb_raise_smem_limit(kernel, smem_bytes);
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
   err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, (int)k.block, smem_bytes);
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaOccupancyMaxActiveBlocksPerMultiprocessor: ") + cudaGetErrorString(err));
   return REBOP_OK;
 }
 
-int rb_jit_launch(const RbJitKernel& k, bool dynamic, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
+int rb_jit_launch(const RbJitKernel& k, int mode, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
                   cudaStream_t stream) {
-  void* kernel = dynamic ? k.kernel_dyn : k.kernel;
-  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  void* kernel = k.grid_kernel[mode];
+  cudaError_t err = rb_raise_smem_limit(kernel, smem_bytes);
   if (err != cudaSuccess) return rb_fail(REBOP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
   void* args[] = {const_cast<SsaRunParams*>(&p)};
   err = cudaLaunchKernel(kernel, dim3(grid), dim3(k.block), args, smem_bytes, stream);

@@ -10,8 +10,7 @@
 #include "ssa_params.h"
 
 struct RbJitKernel {
-  void* kernel = nullptr;      // cudaKernel_t / __global__ function: static schedule
-  void* kernel_dyn = nullptr;  // dynamic schedule
+  void* grid_kernel[3] = {nullptr, nullptr, nullptr};  // cudaKernel_t / __global__ function per RB_MODE_* schedule
   void* kernel_evc = nullptr;  // event-log mode: counting pass (filled by rb_jit_get_events / rb_prebuilt_get)
   void* kernel_evw = nullptr;  // event-log mode: writing pass
   unsigned block = 128;
@@ -26,6 +25,9 @@ struct RbJitKernel {
 int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out);
 // Same for the event-log kernels (a separate NVRTC program, compiled on first use).
 int rb_jit_get_events(const rebop_network& net, int device, RbJitKernel* out);
+// cudaFuncAttributeMaxDynamicSharedMemorySize of `kernel` on the current device, only ever raised (batches on
+// several host threads share the kernels: lowering the limit under a concurrent launch would make it fail).
+cudaError_t rb_raise_smem_limit(const void* kernel, size_t smem_bytes);
 // Launch of an arbitrary entry point of a specialised kernel.
 int rb_jit_launch_entry(void* kernel, unsigned block, const SsaRunParams& p, unsigned grid, size_t smem_bytes, cudaStream_t stream);
 // The kernel rebop_sysgen + nvcc compiled for this network at build time, if any (REBOP_ERR_INVALID if none).
@@ -33,6 +35,6 @@ int rb_prebuilt_get(const rebop_network& net, RbJitKernel* out);
 // Source (and optionally the sm_100a cubin) of the specialised kernel; needs no GPU.
 int rb_jit_compile(const rebop_network& net, std::string* source, std::vector<char>* cubin);
 // Resident CTAs per SM of the kernel with this much dynamic shared memory.
-int rb_jit_occupancy(const RbJitKernel& k, bool dynamic, size_t smem_bytes, int* ctas_per_sm);
-int rb_jit_launch(const RbJitKernel& k, bool dynamic, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
+int rb_jit_occupancy(const RbJitKernel& k, int mode, size_t smem_bytes, int* ctas_per_sm);
+int rb_jit_launch(const RbJitKernel& k, int mode, const SsaRunParams& p, unsigned grid, size_t smem_bytes,
                   cudaStream_t stream);

@@ -7,8 +7,9 @@ typedef long long rb_i64;
 typedef unsigned int rb_u32;
 
 #define RB_FULL_MASK 0xffffffffu
-// Static shared memory of the ensemble loop (ziggurat tables: 256 (X[i], X[i+1]) pairs, 258 F, 256 chord slopes)
-#define RB_STATIC_SMEM_BYTES ((512 + 258 + 256) * 8)
+// Static shared memory of the ensemble loop (ziggurat tables: 256 (X[i], X[i+1]) pairs, 256 (F[i], F[i+1]) pairs,
+// 256 chord slopes)
+#define RB_STATIC_SMEM_BYTES ((512 + 512 + 256) * 8)
 
 // Rate constants carried in the launch parameters (bounds the reactions a specialised kernel can have).
 #define RB_MAX_K 1024
@@ -23,13 +24,29 @@ typedef unsigned int rb_u32;
 
 // Status bits written to SsaRunParams::status.
 #define RB_STATUS_ITER_CAP 1u  // a trajectory hit max_iters before reaching its last grid point
+#define RB_STATUS_NARROW 2u    // a sample did not fit the requested narrow sample type (rb_samples_finish)
+
+// SsaRunParams::progress[traj]: grid points of the current call the trajectory has written itself so far (low 31
+// bits) and whether it has reached the call's last grid point (bit 31).  Zeroed by the engine before a fresh
+// call; a launch that follows REBOP_ERR_ITER_CAP reads it (SsaRunParams::resuming) so that every trajectory
+// continues exactly where it stopped and finished ones are left alone.  A trajectory that reached an absorbing
+// state stops writing rows: every later grid point repeats its last row (rb_samples_finish fills them in).
+#define RB_PROGRESS_DONE 0x80000000u
+#define RB_PROGRESS_ROWS 0x7fffffffu
+
+// Schedules = compile-time variants of the ensemble loop (rb_ssa_loop<Net, MODE>).
+#define RB_MODE_STATIC 0  // thread n runs trajectory n; samples ring-staged, written as [step][row][trajectory] lines
+#define RB_MODE_SPARSE 1  // lanes claim trajectories; both random words drawn ahead of the propensities (few samples per event)
+#define RB_MODE_DENSE 2   // lanes claim trajectories; the uniform is drawn once the event is known to fire (many samples per event)
 
 // Launch parameters (passed by value; lives in the constant bank).
 struct SsaRunParams {
   int* x;                // [S][ldn] species counts, trajectory-contiguous
   double* t;             // [ldn] current time of each trajectory
   rb_u64* rng;           // [4][ldn] xoshiro256++ state (seeded by the engine's rb_seed_kernel before the first launch)
-  int* out;              // [(step-step_first)][n_save][ldn] samples, or null
+  int* out;              // samples, or null.  static: [(step-step_first)][n_save][ldn].  lanes-claim-trajectories
+                         // schedules: raw rows [traj][step-step_first][n_save], one contiguous record per trajectory
+                         // (rb_samples_finish transposes them into [step][row][trajectory])
   rb_u64* events;        // [0] += applied reactions; [2] += lane slots (32 x loop iterations of each warp)
   rb_u32* status;        // [1] |= RB_STATUS_*
   double tmax;
@@ -39,8 +56,10 @@ struct SsaRunParams {
   rb_u32 step_first, step_last;  // grid points handled by this launch (inclusive)
   rb_u32 n_save;         // rows per sample
   rb_u32 ring_depth;     // power of two, 1..32: grid points a warp can stage in shared memory
-  rb_u32 max_iters;      // per-trajectory loop-iteration cap for this launch (0 = 2^32-1)
+  rb_u32 max_iters;      // per-trajectory loop-iteration cap for this launch, rounded up to whole ticks (0 = none)
   rb_u32 dynamic;        // 1: lanes claim further trajectories from *work_next when theirs is finished (ring_depth must be 0)
+  rb_u32 resuming;       // 1: this launch continues a call cut short by the watchdog: start from progress[]
+  rb_u32* progress;      // [ldn] see RB_PROGRESS_*
   rb_u32 n_launched;     // dynamic: threads of the grid = trajectories assigned statically at the start
   rb_u32* work_next;     // dynamic: [1] trajectories claimed beyond n_launched (zero before the launch)
   rb_u32 bias_hi;        // 0x43300000: high word of the biased-double species form (opaque to the compiler on purpose)
@@ -55,7 +74,11 @@ struct SsaRunParams {
   const rb_u64* ev_offsets;  // [n_traj] first row of each trajectory (read by the writing pass)
   double* ev_times;          // [ev_total] time of every row
   rb_u64 ev_total;           // rows of the whole ensemble = stride of the sample rows in `out`
+  rb_u32 ev_single;          // 1: exactly one _advance_one_reaction per trajectory whatever its time, nothing logged
+                             // (Gillespie::advance_one_reaction, src/gillespie.rs:270-274)
   const rb_u32* gtab;    // table-driven and large specialised kernels: per-reaction records (+ saved-species list)
+  const void* tables;    // table-driven kernel: this batch's RbTables image in global memory
+  int n_species, n_reactions, arith;  // table-driven kernel: copies of the RbTables scalars
   double k[RB_MAX_K];    // specialised kernels: rate constants (kernel parameters may be up to 32 KB on sm_70+)
 };
 

@@ -1,9 +1,12 @@
 // ssa_table.cu -- K1: table-driven direct-method kernel (any network, no JIT).
 //
-// Species counts live in shared memory (one column per thread, conflict-free),
-// rate constants / reactant terms / stoichiometry / expression byte-code sit in
-// __constant__ memory and are read warp-uniformly (every lane evaluates reaction
-// r at the same time, so each fetch is a broadcast).
+// Species counts live in shared memory (one column per thread, conflict-free).  The network is
+// data: one 16-byte record per reaction for the common mass-action case (SsaRunParams::gtab), and
+// the batch's own RbTables image in global memory (SsaRunParams::tables: CSR reactant terms,
+// stoichiometry, expression byte-code) for everything else.  Both are read at warp-uniform
+// addresses (every lane evaluates reaction r at the same time), so each fetch is a broadcast out
+// of L1.  Nothing is process-global: batches with different networks may run side by side on one
+// device from different host threads and streams.
 //
 // Replaces: Gillespie::advance_until + the pyo3 grid loop
 // (src/gillespie.rs:315-344, src/pyo3_gillespie.rs:197-208) with Rate::rate
@@ -15,23 +18,27 @@
 #include "rb_tables.h"
 #include "ssa_kernel.cuh"
 #include "ssa_table.h"
-
-__constant__ RbTables c_tab;
+#include "jit.hpp"
 
 struct RbTableNet {
   static constexpr int BLOCK = RB_TABLE_BLOCK;
   int* xs;  // this thread's column: species s at xs[s * BLOCK]
+  const RbTables* __restrict__ tab;
+  int n_reactions, arith;
 
-  static __device__ __forceinline__ int smem_words(const SsaRunParams&) {
-    return c_tab.n_species * BLOCK;
+  static __device__ __forceinline__ int smem_words(const SsaRunParams& p) { return p.n_species * BLOCK; }
+  __device__ __forceinline__ void init(const SsaRunParams& p, int* smem, rb_u32 tid, rb_u32) {
+    xs = smem + tid;
+    tab = static_cast<const RbTables*>(p.tables);
+    n_reactions = p.n_reactions;
+    arith = p.arith;
   }
-  __device__ __forceinline__ void init(const SsaRunParams&, int* smem, rb_u32 tid, rb_u32) { xs = smem + tid; }
   __device__ __forceinline__ void load(const SsaRunParams& p, rb_u32 traj, bool valid) {
-    const int S = c_tab.n_species;
+    const int S = p.n_species;
     for (int s = 0; s < S; ++s) xs[s * BLOCK] = valid ? p.x[(size_t)s * p.ldn + traj] : 0;
   }
   __device__ __forceinline__ void store(const SsaRunParams& p, rb_u32 traj) {
-    const int S = c_tab.n_species;
+    const int S = p.n_species;
     for (int s = 0; s < S; ++s) p.x[(size_t)s * p.ldn + traj] = xs[s * BLOCK];
   }
 
@@ -40,11 +47,11 @@ struct RbTableNet {
     double stack[RB_EXPR_STACK];
     int sp = 0;
     for (int i = lo; i < hi; ++i) {
-      const int op = c_tab.op_code[i];
+      const int op = __ldg(&tab->op_code[i]);
       if (op == RB_OP_CONST) {
-        stack[sp++] = c_tab.op_val[i];
+        stack[sp++] = __ldg(&tab->op_val[i]);
       } else if (op == RB_OP_SPECIES) {
-        stack[sp++] = rb_i2d(xs[c_tab.op_idx[i] * BLOCK]);
+        stack[sp++] = rb_i2d(xs[__ldg(&tab->op_idx[i]) * BLOCK]);
       } else if (op == RB_OP_NEG) {
         stack[sp - 1] = -stack[sp - 1];
       } else if (op == RB_OP_EXP) {
@@ -84,12 +91,12 @@ struct RbTableNet {
 
   // Rate::rate for reaction r through the CSR tables in constant memory (any number of terms, expressions).
   __device__ __noinline__ double rate_general(int r) const {
-    const int e0 = c_tab.expr_ptr[r], e1 = c_tab.expr_ptr[r + 1];
+    const int e0 = __ldg(&tab->expr_ptr[r]), e1 = __ldg(&tab->expr_ptr[r + 1]);
     if (e1 > e0) return eval_expr(e0, e1);
-    double acc = c_tab.k[r];
-    const int j1 = c_tab.term_ptr[r + 1];
-    for (int j = c_tab.term_ptr[r]; j < j1; ++j)
-      acc = term(acc, xs[c_tab.term_idx[j] * BLOCK], c_tab.term_exp[j], c_tab.arith);
+    double acc = __ldg(&tab->k[r]);
+    const int j1 = __ldg(&tab->term_ptr[r + 1]);
+    for (int j = __ldg(&tab->term_ptr[r]); j < j1; ++j)
+      acc = term(acc, xs[__ldg(&tab->term_idx[j]) * BLOCK], __ldg(&tab->term_exp[j]), arith);
     return acc;
   }
 
@@ -101,14 +108,14 @@ struct RbTableNet {
     const rb_u32 n = (w.w >> 16) & 0xffu;
     if (n == 0xffu) return rate_general(r);
     double acc = __hiloint2double((int)w.y, (int)w.x);
-    if (n >= 1u) acc = term(acc, xs[(w.z & 0xffffu) * BLOCK], (int)(w.w & 0xffu), c_tab.arith);
-    if (n >= 2u) acc = term(acc, xs[(w.z >> 16) * BLOCK], (int)((w.w >> 8) & 0xffu), c_tab.arith);
+    if (n >= 1u) acc = term(acc, xs[(w.z & 0xffffu) * BLOCK], (int)(w.w & 0xffu), arith);
+    if (n >= 2u) acc = term(acc, xs[(w.z >> 16) * BLOCK], (int)((w.w >> 8) & 0xffu), arith);
     return acc;
   }
 
   // make_cumrates (src/gillespie.rs:357-364); only the total is kept, select() re-walks the sum.
   __device__ __forceinline__ double propensities(const SsaRunParams& p) const {
-    const int R = c_tab.n_reactions;
+    const int R = n_reactions;
     const uint4* rec = reinterpret_cast<const uint4*>(p.gtab);
     double total = 0.0;
 #pragma unroll 4
@@ -117,11 +124,11 @@ struct RbTableNet {
   }
 
   __device__ __forceinline__ int select(const SsaRunParams& p, double chosen) const {
-    const int R = c_tab.n_reactions;
+    const int R = n_reactions;
     const uint4* rec = reinterpret_cast<const uint4*>(p.gtab);
     double cum = 0.0;
     int i;
-    if (c_tab.arith == 0) {
+    if (arith == 0) {
       // choose_cumrate_sum (src/gillespie.rs:402-407): the index is a count
       i = 0;
 #pragma unroll 4
@@ -143,10 +150,11 @@ struct RbTableNet {
     return i;  // R: nothing matches (macro arithmetic), or no reactions at all
   }
 
-  static __device__ __forceinline__ int none() { return c_tab.n_reactions; }
+  __device__ __forceinline__ int none() const { return n_reactions; }
 
-  __device__ __forceinline__ bool apply(const SsaRunParams& p, int i) {
-    if (i >= c_tab.n_reactions) return false;
+  __device__ __forceinline__ void apply(const SsaRunParams& p, int i, rb_u32& nev) {
+    if (i >= n_reactions) return;
+    ++nev;
     const uint4* rec = reinterpret_cast<const uint4*>(p.gtab);
     const uint4 j = __ldg(rec + 2 * i + 1);
     if ((__ldg(rec + 2 * i).w >> 24) == 0u) {
@@ -158,26 +166,31 @@ struct RbTableNet {
       for (int q = 0; q < 4; ++q)
         if (diff[q] != 0) xs[idx[q] * BLOCK] += diff[q];
     } else {
-      const int j1 = c_tab.jump_ptr[i + 1];
-      for (int q = c_tab.jump_ptr[i]; q < j1; ++q) xs[c_tab.jump_idx[q] * BLOCK] += c_tab.jump_diff[q];
+      const int j1 = __ldg(&tab->jump_ptr[i + 1]);
+      for (int q = __ldg(&tab->jump_ptr[i]); q < j1; ++q) xs[__ldg(&tab->jump_idx[q]) * BLOCK] += __ldg(&tab->jump_diff[q]);
     }
-    return true;
   }
 
   __device__ __forceinline__ void record(const SsaRunParams& p, int* dst, rb_u32 stride) const {
-    for (rb_u32 j = 0; j < p.n_save; ++j) dst[(size_t)j * stride] = xs[c_tab.save_idx[j] * BLOCK];
+    const rb_u32* save = p.gtab + n_reactions * RB_GTAB_WORDS_PER_REACTION;  // saved-species list behind the records
+    for (rb_u32 j = 0; j < p.n_save; ++j) dst[(size_t)j * stride] = xs[__ldg(save + j) * BLOCK];
   }
 };
 
 __global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel(const __grid_constant__ SsaRunParams p) {
   extern __shared__ __align__(16) int rb_smem[];
   RbTableNet net;
-  rb_ssa_loop<RbTableNet, false>(net, p, rb_smem);
+  rb_ssa_loop<RbTableNet, RB_MODE_STATIC>(net, p, rb_smem);
 }
 __global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel_dyn(const __grid_constant__ SsaRunParams p) {
   extern __shared__ __align__(16) int rb_smem[];
   RbTableNet net;
-  rb_ssa_loop<RbTableNet, true>(net, p, rb_smem);
+  rb_ssa_loop<RbTableNet, RB_MODE_SPARSE>(net, p, rb_smem);
+}
+__global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel_dns(const __grid_constant__ SsaRunParams p) {
+  extern __shared__ __align__(16) int rb_smem[];
+  RbTableNet net;
+  rb_ssa_loop<RbTableNet, RB_MODE_DENSE>(net, p, rb_smem);
 }
 
 __global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel_evc(const __grid_constant__ SsaRunParams p) {
@@ -191,32 +204,30 @@ __global__ void __launch_bounds__(RB_TABLE_BLOCK) rb_ssa_table_kernel_evw(const 
   rb_ssa_events<RbTableNet, true>(net, p, rb_smem);
 }
 
+typedef void (*RbTableKernel)(const SsaRunParams);
+static RbTableKernel grid_kernel(int mode) {
+  return mode == RB_MODE_STATIC ? rb_ssa_table_kernel : mode == RB_MODE_SPARSE ? rb_ssa_table_kernel_dyn : rb_ssa_table_kernel_dns;
+}
+
 // Event-log mode: counting (write = false) or writing pass.
-cudaError_t rb_table_launch_events(const RbTables* host_tables, bool write, const SsaRunParams& p, unsigned grid,
-                                   size_t smem_bytes, cudaStream_t stream) {
+cudaError_t rb_table_launch_events(bool write, const SsaRunParams& p, unsigned grid, size_t smem_bytes, cudaStream_t stream) {
   auto kernel = write ? rb_ssa_table_kernel_evw : rb_ssa_table_kernel_evc;
-  cudaError_t err = cudaMemcpyToSymbolAsync(c_tab, host_tables, sizeof(RbTables), 0, cudaMemcpyHostToDevice, stream);
-  if (err != cudaSuccess) return err;
-  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  cudaError_t err = rb_raise_smem_limit(reinterpret_cast<const void*>(kernel), smem_bytes);
   if (err != cudaSuccess) return err;
   kernel<<<grid, RB_TABLE_BLOCK, smem_bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t rb_table_occupancy(bool dynamic, size_t smem_bytes, int* ctas_per_sm) {
-  auto kernel = dynamic ? rb_ssa_table_kernel_dyn : rb_ssa_table_kernel;
-  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+cudaError_t rb_table_occupancy(int mode, size_t smem_bytes, int* ctas_per_sm) {
+  auto kernel = grid_kernel(mode);
+  cudaError_t err = rb_raise_smem_limit(reinterpret_cast<const void*>(kernel), smem_bytes);
   if (err != cudaSuccess) return err;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, kernel, RB_TABLE_BLOCK, smem_bytes);
 }
 
-cudaError_t rb_table_launch(const RbTables* host_tables, bool dynamic, const SsaRunParams& p, unsigned grid,
-                            size_t smem_bytes, cudaStream_t stream) {
-  auto kernel = dynamic ? rb_ssa_table_kernel_dyn : rb_ssa_table_kernel;
-  cudaError_t err = cudaMemcpyToSymbolAsync(c_tab, host_tables, sizeof(RbTables), 0,
-                                            cudaMemcpyHostToDevice, stream);
-  if (err != cudaSuccess) return err;
-  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+cudaError_t rb_table_launch(int mode, const SsaRunParams& p, unsigned grid, size_t smem_bytes, cudaStream_t stream) {
+  auto kernel = grid_kernel(mode);
+  cudaError_t err = rb_raise_smem_limit(reinterpret_cast<const void*>(kernel), smem_bytes);
   if (err != cudaSuccess) return err;
   kernel<<<grid, RB_TABLE_BLOCK, smem_bytes, stream>>>(p);
   return cudaGetLastError();

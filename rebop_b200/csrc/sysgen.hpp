@@ -35,8 +35,7 @@ int rb_system_network(const rebop_system& sys, const double* params, size_t n_pa
 // source text the run-time generator would produce for the same network.
 struct RbPrebuilt {
   const char* key;      // rb_codegen_source(net, "rb_ssa_jit") of the network it was generated from
-  const void* kernel;   // __global__ function, static schedule
-  const void* kernel_dyn;  // dynamic schedule
+  const void* grid_kernel[3];  // __global__ functions of the time-grid loop, one per RB_MODE_* schedule
   const void* kernel_evc;  // event-log mode: counting pass
   const void* kernel_evw;  // event-log mode: writing pass
   unsigned block, static_smem, net_words;

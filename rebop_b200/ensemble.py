@@ -9,12 +9,11 @@ result independent of the reduction order and of the GPU count.
 
 Two ways to use several GPUs:
   * one process per GPU under torch.distributed (bench.py): `shard_range` + `allreduce_sums`;
-  * one process, several devices: `run_sharded` drives one host thread per device (the C ABI calls
-    release the GIL), which is what `Gillespie.run(..., devices=[...])` uses.
+  * one process, several devices: `run_sharded` drives the C ABI's ensemble handle (rebop_ensemble_*: one host
+    worker thread per device inside the library, NCCL all-reduce of the sums), which is what
+    `Gillespie.run(..., devices=[...])` uses.
 """
 from __future__ import annotations
-
-import threading
 
 import numpy as np
 
@@ -75,50 +74,27 @@ def device_sums_as_tensor(batch: "_ffi.Batch", device: int):
 
 
 def run_sharded(net: "_ffi.Network", n_total: int, x0, seeds, tmax: float, nb_steps: int, save_idx, devices,
-                kernel: int = _ffi.KERNEL_AUTO, out: np.ndarray | None = None, want_samples: bool = True):
-    """Simulate n_total trajectories split over `devices`, one host thread per device.
+                kernel: int = _ffi.KERNEL_AUTO, out: np.ndarray | None = None, want_samples: bool = True,
+                want_sums: bool = True, dtype=np.int32):
+    """Simulate n_total trajectories split over `devices` through the C ABI's ensemble handle
+    (rebop_ensemble_*: one batch and one host worker thread per device, contiguous trajectory ranges).
 
-    seeds: uint64 [n_total].  Returns (samples int32 [nb_steps+1][n_save][n_total] or None,
-    sums int64 [rows], sumsq uint64 [rows], events, kernel_ms_max).
+    seeds: uint64 [n_total].  Returns (samples [nb_steps+1][n_save][n_total] of `dtype` or None,
+    sums int64 [rows] or None, sumsq uint64 [rows] or None, events, kernel_ms_max); the sums are the exact integer
+    row sums, all-reduced over the devices with NCCL inside the library when there is more than one.
     """
     devices = list(devices)
-    ranges = shard_ranges(n_total, len(devices))
     n_save = net.n_species if save_idx is None else len(save_idx)
     rows = (nb_steps + 1) * n_save
+    dtype = np.dtype(dtype)
     if want_samples and out is None:
-        out = np.empty((nb_steps + 1, n_save, n_total), dtype=np.int32)
-    results: list = [None] * len(devices)
-
-    def work(i):
-        lo, cnt = ranges[i]
-        if cnt == 0:
-            results[i] = (np.zeros(rows, np.int64), np.zeros(rows, np.uint64), 0, 0.0)
-            return
-        try:
-            b = _ffi.Batch(net, cnt, x0, seeds=seeds[lo:lo + cnt], device=devices[i], kernel=kernel)
-            try:
-                b.run_grid(tmax, nb_steps, save_idx=save_idx)
-                if want_samples and rows:
-                    b.samples_into(out, lo)  # straight into this shard's columns of the result
-                s1, s2 = b.sample_sums() if rows else (np.zeros(0, np.int64), np.zeros(0, np.uint64))
-                results[i] = (s1, s2, b.events()[1], b.last_kernel_ms)
-            finally:
-                b.close()
-        except BaseException as e:  # noqa: BLE001 - re-raised in the caller's thread
-            results[i] = e
-
-    if len(devices) == 1:
-        work(0)
-    else:
-        threads = [threading.Thread(target=work, args=(i,)) for i in range(len(devices))]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-    for r in results:
-        if isinstance(r, BaseException):
-            raise r
-    sums = sum(r[0] for r in results)
-    sumsq = sum(r[1] for r in results)
-    events = sum(r[2] for r in results)
-    return out if want_samples else None, sums, sumsq, events, max(r[3] for r in results)
+        out = np.empty((nb_steps + 1, n_save, n_total), dtype=dtype)
+    e = _ffi.Ensemble(net, n_total, x0, devices, seeds=seeds, kernel=kernel, dtype=dtype)
+    try:
+        e.run_grid(tmax, nb_steps, save_idx=save_idx, host_out=out if (want_samples and rows) else None)
+        sums = sumsq = None
+        if want_sums and rows:
+            sums, sumsq = e.sums()
+        return out if want_samples else None, sums, sumsq, e.events()[1], e.last_kernel_ms
+    finally:
+        e.close()

@@ -207,8 +207,9 @@ class Gillespie:
         device, devices, kernel, dtype
             CUDA device index, or a list of devices the trajectories are sharded over (contiguous
             ranges, one host thread per device; results do not depend on the sharding);
-            "auto" | "nvrtc" | "table"; dtype of the returned counts (np.int64 like the reference,
-            or np.int32 to halve the host copy).
+            "auto" | "nvrtc" | "table"; dtype of the returned counts: np.int64 like the reference, np.int32, or
+            np.int16 (the samples are produced in that type on the device, so a narrower type shrinks the
+            device-to-host copy; a count that does not fit int16 raises instead of wrapping).
         reduce : bool
             Return the ensemble mean and variance of every saved species at every sample time
             (variables ``<name>_mean`` and ``<name>_var``, dim ``time``) instead of the
@@ -261,8 +262,11 @@ class Gillespie:
             devs = [device] if devices is None else list(devices)
             # rows come back in the order requested; duplicates are allowed like in the reference
             uniq = sorted({self._species[v] for v in save_names})
+            sample_dtype = np.dtype(dtype) if np.dtype(dtype) in (np.dtype(np.int16), np.dtype(np.int32), np.dtype(np.int64)) \
+                else np.dtype(np.int32)
             samples, sums, sumsq, self.last_events, self.last_kernel_ms = ensemble.run_sharded(
-                net, n, x0, seeds, tmax, nb_steps, uniq, devs, kernel=_KERNELS[kernel], want_samples=not reduce)
+                net, n, x0, seeds, tmax, nb_steps, uniq, devs, kernel=_KERNELS[kernel], want_samples=not reduce,
+                want_sums=reduce, dtype=sample_dtype)
             row = {idx: j for j, idx in enumerate(uniq)}
             if reduce:
                 mean, var = ensemble.finalize_stats(sums, sumsq, n)

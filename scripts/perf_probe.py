@@ -29,8 +29,10 @@ for rep in range(2):
     wall = time.time() - t0
     ev = b.events()[1]
     ms = b.last_kernel_ms
-    print(f"{name} n={n} kernel={b.kernel_used} arith={arith} tmax={tmax} nb={nb}: events={ev:.4g} ({ev / n:.1f}/traj) "
-          f"kernel={ms:.1f} ms wall={wall * 1e3:.1f} ms -> {ev / ms * 1e3:.4g} events/s, {n / ms * 1e3:.4g} traj/s, "
+    fin = b.last_finish_ms
+    print(f"{name} n={n} kernel={b.kernel_used} sched={b.schedule_used} arith={arith} tmax={tmax} nb={nb}: events={ev:.4g} "
+          f"({ev / n:.1f}/traj) loop={ms:.2f} ms finish={fin:.2f} ms wall={wall * 1e3:.1f} ms -> {ev / ms * 1e3:.4g} events/s "
+          f"(loop), {ev / (ms + fin) * 1e3:.4g} (loop+finish), {n / (ms + fin) * 1e3:.4g} traj/s, "
           f"lane eff {ev / max(b.lane_slots, 1):.3f}", flush=True)
     b.close()
 if len(sys.argv) <= 7:

@@ -286,7 +286,7 @@ def test_generated_kernels_fit_their_register_budget_without_spills(ffi, tmp_pat
     cubin.write_bytes(net.jit_cubin())
     usage = subprocess.check_output(["cuobjdump", "-res-usage", str(cubin)], text=True)
     found = re.findall(r"Function (rb_ssa_jit\w*):\s*\n\s*REG:(\d+) STACK:(\d+)", usage)
-    assert {f[0] for f in found} == {"rb_ssa_jit", "rb_ssa_jit_dyn"}
+    assert {f[0] for f in found} == {"rb_ssa_jit", "rb_ssa_jit_dyn", "rb_ssa_jit_dns"}
     for fn, regs, stack in found:
         assert int(regs) <= max_regs, (fn, regs)
         assert int(stack) == 0, (fn, "spills", stack)

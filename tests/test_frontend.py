@@ -74,7 +74,8 @@ def test_lowering_errors_and_tables(ffi):
     d = rebop_b200.Gillespie()
     d.add_reaction(0.001, ["A", "A"], ["B"])
     src = d._lower({}, ffi.ARITH_API).codegen()
-    assert "__dsub_rn(d0, 1.0)" in src and "0x000001fe" in src  # falling-factorial factor; packed jump: -2 = 0xfe, +1 = 0x01
+    # falling-factorial factor; packed jump: -2 = 0xfe, +1 = 0x01, and the event-count lane (1) behind the species
+    assert "__dsub_rn(d0, 1.0)" in src and "0x000101fe" in src
 
 
 # ---- GPU: the reference's tests -----------------------------------------------------------------

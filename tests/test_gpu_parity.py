@@ -147,7 +147,7 @@ def test_conservation_and_bounds(gpu, ffi, kernel):
     assert (out[-1, 0] == 1).all() and (out[-1, 2] > 1000).all() and (out[-1, 3] < 10000).all()
 
 
-@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("schedule", [1, 2, 3])
 @pytest.mark.parametrize("kernel", ["table", "nvrtc"])
 def test_nan_rate_freezes(gpu, ffi, kernel, schedule):
     """src/gillespie_macro.rs:224-238: a NaN rate constant => no reaction, t = tmax."""
@@ -162,7 +162,7 @@ def test_nan_rate_freezes(gpu, ffi, kernel, schedule):
     assert b.events()[0] == 0
 
 
-@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("schedule", [1, 2, 3])
 @pytest.mark.parametrize("kernel", ["table", "nvrtc"])
 def test_no_reactions(gpu, ffi, kernel, schedule):
     """src/gillespie_macro.rs:239-253."""
@@ -188,7 +188,7 @@ def test_sample_sums(gpu, ffi, kernel):
     np.testing.assert_array_equal(s2.reshape(21, 3).astype(np.int64), (out * out).sum(axis=2))
 
 
-@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("schedule", [1, 2, 3])
 @pytest.mark.parametrize("kernel", ["table", "nvrtc"])
 def test_iteration_cap_is_reported(gpu, ffi, oracle, kernel, schedule):
     """The watchdog stops a launch between two passes; advance_until can then simply be called again and ends
@@ -216,24 +216,66 @@ def test_iteration_cap_is_reported(gpu, ffi, oracle, kernel, schedule):
     assert (b.times() == 0.05).all()
 
 
-@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
-def test_golden_fixtures(gpu, ffi, kernel):
+@pytest.mark.parametrize("schedule", [1, 2, 3])
+@pytest.mark.parametrize("kernel", ["table", "nvrtc", "prebuilt"])
+def test_golden_fixtures(gpu, ffi, kernel, schedule):
     """Committed fixtures (tests/golden/, full-length runs incl. Vilar to t=200 and the reference's
-    rng=42 vector): final states, per-run event totals and a checksum over every sample."""
+    rng=42 vector): final states, per-run event totals and a checksum over every sample -- for every kernel
+    family (the build-time kernels wherever one matches the fixture's network) in both schedules."""
     import json
     import os
 
     gdir = os.path.join(os.path.dirname(__file__), "golden")
     files = sorted(f for f in os.listdir(gdir) if f.endswith(".json"))
     assert files
+    ran = 0
     for f in files:
         g = json.load(open(os.path.join(gdir, f)))
         model = models.MODELS[g["model"]]()
+        net = models.build_network(model, g["arith"])
+        if kernel == "prebuilt" and not net.has_prebuilt:
+            continue
         seeds = np.array(g["seeds"], dtype=np.uint64)
-        out, ev, _ = run_product(ffi, model, seeds, g["tmax"], g["nb_steps"], KERNELS[kernel], g["arith"])
+        b = ffi.Batch(net, len(seeds), model["x0"], seeds=seeds, kernel={"table": 1, "nvrtc": 2, "prebuilt": 3}[kernel])
+        b.set_schedule(schedule)
+        b.run_grid(g["tmax"], g["nb_steps"])
+        out, ev = b.samples(), b.events()[0]
+        assert b.schedule_used == schedule and b.kernel_used == {"table": 1, "nvrtc": 2, "prebuilt": 3}[kernel]
+        b.close()
         assert out[-1].T.tolist() == g["final"], f
         assert ev == sum(g["events"]), f
         assert int(out.astype(np.int64).sum()) == g["checksum"], f
+        ran += 1
+    assert ran >= (2 if kernel == "prebuilt" else len(files))  # vilar_macro_full and dimers_macro have build-time kernels
+
+
+@pytest.mark.parametrize("kernel", ["prebuilt", "nvrtc"])
+def test_headline_configuration_bit_exact(gpu, ffi, oracle, kernel):
+    """The benchmarked combination itself (bench.py, BASELINE config C4): Vilar in define_system! arithmetic on
+    the build-time kernel, dynamic schedule, t = 0..200 with 201 samples, more trajectories than resident lanes
+    (148 SMs x 5 CTAs x 128 lanes = 94 720), so lanes claim further trajectories from the work counter.  The
+    first 1024 trajectories and a strided subsample (the claimed ones included) are compared with the oracle on
+    all 201 x 9 samples; the whole ensemble is checked through the event total of the subsample and through
+    invariants of the network (gene copies conserved)."""
+    model = models.vilar()
+    n = 121_000
+    net = models.build_network(model, 1)
+    b = ffi.Batch(net, n, model["x0"], seeds=None, seed_base=0, kernel={"prebuilt": 3, "nvrtc": 2}[kernel])
+    b.set_schedule(2)
+    b.run_grid(200.0, 200)
+    assert b.schedule_used == 2
+    out = b.samples()
+    b.close()
+    head = models.seeds_sequence(1024)
+    ref, _, _ = oracle.run_batch_macro("vilar", model["params"], model["x0"], head, 200.0, 200, threads=16)
+    np.testing.assert_array_equal(out[:, :, :1024], ref)
+    stride = 118
+    sub = np.arange(1024 + 7, n, stride, dtype=np.uint64)  # 1017 trajectories, most of them claimed dynamically
+    ref, _, _ = oracle.run_batch_macro("vilar", model["params"], model["x0"], sub, 200.0, 200, threads=16)
+    np.testing.assert_array_equal(out[:, :, 1024 + 7::stride], ref)
+    # Da + Dpa = 1 and Dr + Dpr = 1 for every trajectory at every sample
+    assert (out[:, 0] + out[:, 2] == 1).all() and (out[:, 1] + out[:, 3] == 1).all()
+    assert (out >= 0).all()
 
 
 def test_full_size_properties(gpu, ffi):
@@ -270,7 +312,7 @@ def test_full_size_properties(gpu, ffi):
     ("mm_lma", 1000, 100.0, 20),
     ("vilar", 96, 10.0, 10),
 ])
-@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("schedule", [1, 2, 3])
 def test_both_variants_bit_exact_vs_oracle(gpu, ffi, oracle, kernel, arith, name, n, tmax, nb_steps, schedule):
     """Both variants of every kernel, forced: static (ring-staged samples, uniform from a copy of the stream)
     and dynamic (draws made ahead of the propensities, stream stepped back on crossings and absorbing states,
@@ -300,7 +342,7 @@ def test_dynamic_schedule_is_bit_exact(gpu, ffi, oracle, kernel):
     ref, _, tot = oracle_network(oracle, model).run_batch(model["x0"], seeds, 60.0, 6, threads=8)
     net = models.build_network(model)
     outs = {}
-    for schedule in (1, 2):
+    for schedule in (1, 2, 3):
         b = ffi.Batch(net, n, model["x0"], seeds=seeds, kernel=KERNELS[kernel])
         b.set_schedule(schedule)
         b.run_grid(60.0, 6)
@@ -308,8 +350,8 @@ def test_dynamic_schedule_is_bit_exact(gpu, ffi, oracle, kernel):
         assert b.events()[0] == tot
         outs[schedule] = b.samples()
         b.close()
-    np.testing.assert_array_equal(outs[1], ref)
-    np.testing.assert_array_equal(outs[2], ref)
+    for schedule in (1, 2, 3):
+        np.testing.assert_array_equal(outs[schedule], ref)
 
 
 def test_dynamic_schedule_resumes_exactly(gpu, ffi, oracle):
@@ -318,16 +360,17 @@ def test_dynamic_schedule_resumes_exactly(gpu, ffi, oracle):
     seeds = models.seeds_sequence(n, first=1)
     net = models.build_network(model, 1)
     finals = {}
-    for schedule in (1, 2):
+    for schedule in (1, 2, 3):
         b = ffi.Batch(net, n, model["x0"], seeds=seeds)
         b.set_schedule(schedule)
         for i in range(4):  # the grid loop of the binding, driven by the caller (src/lib.rs:129-133)
             b.advance_until(0.06 * i / 3)
         finals[schedule] = (b.species(), b.times(), b.events()[0])
         b.close()
-    np.testing.assert_array_equal(finals[1][0], finals[2][0])
-    np.testing.assert_array_equal(finals[1][1], finals[2][1])
-    assert finals[1][2] == finals[2][2]
+    for schedule in (2, 3):
+        np.testing.assert_array_equal(finals[1][0], finals[schedule][0])
+        np.testing.assert_array_equal(finals[1][1], finals[schedule][1])
+        assert finals[1][2] == finals[schedule][2]
     ref, _, tot = oracle_network(oracle, model, 1).run_batch(model["x0"], seeds[:2000], 0.06, 3, threads=8)
     np.testing.assert_array_equal(finals[2][0][:2000].T, ref[-1])
 
@@ -442,3 +485,270 @@ def test_segmented_run_with_host_buffer(gpu, ffi, oracle):
     np.testing.assert_array_equal(host[:, :, :2000], ref)
     a.close()
     b.close()
+
+
+# ---- round 2: resume exactness, sample types, single steps, concurrency --------------------------------------------
+
+@pytest.mark.parametrize("schedule", [1, 2, 3])
+@pytest.mark.parametrize("kernel", ["table", "nvrtc"])
+def test_resume_after_iteration_cap_is_stream_exact(gpu, ffi, oracle, kernel, schedule):
+    """Repeating a call the watchdog cut short continues every trajectory where it stopped and leaves finished ones
+    alone: a trajectory already at tmax must not draw again (the reference made ONE advance_until call).  The
+    interval that follows must therefore still match the oracle: species, times and event totals."""
+    model = models.dimers()
+    net = models.build_network(model)
+    n = 96
+    seeds = models.seeds_sequence(n, first=3)
+    ref, _, tot = oracle_network(oracle, model).run_batch(model["x0"], seeds, 0.1, 2, threads=8)  # rows at t = 0, 0.05, 0.1
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds, kernel=KERNELS[kernel])
+    b.set_schedule(schedule)
+    for target, row in ((0.0, 0), (0.05, 1), (0.1, 2)):
+        b.set_max_iters(64)
+        calls = 0
+        while True:
+            calls += 1
+            try:
+                b.advance_until(target)
+                break
+            except ffi.RebopError as e:
+                assert e.status == ffi.ERR_ITER_CAP and calls < 400
+        if target > 0:
+            assert calls > 2
+        np.testing.assert_array_equal(b.species().T, ref[row])
+        assert (b.times() == target).all()
+    assert b.events()[0] == tot
+    b.close()
+
+
+@pytest.mark.parametrize("schedule", [1, 2, 3])
+def test_run_grid_resumes_after_iteration_cap(gpu, ffi, oracle, schedule):
+    """run_grid cut short by the watchdog: the same call again continues from the grid points reached; the samples of
+    the finished call are those of an uninterrupted run."""
+    model = models.sir()
+    net = models.build_network(model)
+    n = 3000
+    seeds = models.seeds_sequence(n, first=9)
+    ref, _, tot = oracle_network(oracle, model).run_batch(model["x0"], seeds, 250.0, 50, threads=8)
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds)
+    b.set_schedule(schedule)
+    b.set_max_iters(128)
+    calls = 0
+    while True:
+        calls += 1
+        try:
+            b.run_grid(250.0, 50)
+            break
+        except ffi.RebopError as e:
+            assert e.status == ffi.ERR_ITER_CAP and calls < 200
+    assert calls > 3
+    np.testing.assert_array_equal(b.samples(), ref)
+    assert b.events()[0] == tot
+    s1, _ = b.sample_sums()
+    np.testing.assert_array_equal(s1.reshape(51, 3), ref.sum(axis=2, dtype=np.int64))
+    b.close()
+
+
+@pytest.mark.parametrize("schedule", [1, 2, 3])
+@pytest.mark.parametrize("dtype", [np.int16, np.int64])
+def test_sample_types(gpu, ffi, oracle, dtype, schedule):
+    """int16 / int64 samples are produced on the device; values, host copies in every type and the row sums agree
+    with the int32 run and the oracle."""
+    model = models.sir()
+    net = models.build_network(model)
+    n = 2100
+    seeds = models.seeds_sequence(n, first=21)
+    ref, _, _ = oracle_network(oracle, model).run_batch(model["x0"], seeds, 250.0, 40, threads=8)
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds)
+    b.set_schedule(schedule)
+    b.set_sample_dtype(dtype)
+    host = np.empty((41, 3, n), dtype=dtype)
+    b.run_grid(250.0, 40, host_out=host)
+    np.testing.assert_array_equal(host, ref.astype(dtype))
+    assert b.samples().dtype == np.dtype(dtype)
+    np.testing.assert_array_equal(b.samples(), ref.astype(dtype))
+    np.testing.assert_array_equal(b.samples(np.int32), ref)
+    np.testing.assert_array_equal(b.samples(np.int64), ref.astype(np.int64))
+    s1, s2 = b.sample_sums()
+    r64 = ref.astype(np.int64)
+    np.testing.assert_array_equal(s1.reshape(41, 3), r64.sum(axis=2))
+    np.testing.assert_array_equal(s2.reshape(41, 3).astype(np.int64), (r64 * r64).sum(axis=2))
+    b.close()
+
+
+@pytest.mark.parametrize("schedule", [1, 3])
+def test_int16_overflow_is_an_error(gpu, ffi, schedule):
+    """A count outside the int16 range must not wrap silently."""
+    net = ffi.Network(1, 0)
+    net.add_reaction_lma_sparse(1.0e5, [], [1])   # 0 -> A at 1e5 per unit time: about 1e5 molecules at t = 1
+    b = ffi.Batch(net, 64, [0], seeds=models.seeds_sequence(64))
+    b.set_schedule(schedule)
+    b.set_sample_dtype(np.int16)
+    with pytest.raises(ffi.RebopError) as e:
+        b.run_grid(1.0, 4)
+    assert e.value.status == ffi.ERR_LIMIT
+    b.set_sample_dtype(np.int32)
+    b.set_species([0])
+    b.set_time(0.0)
+    b.run_grid(1.0, 4)
+    assert (b.samples()[-1] > 90000).all()
+    b.close()
+
+
+@pytest.mark.parametrize("kernel", ["table", "nvrtc", "prebuilt"])
+def test_advance_one_reaction(gpu, ffi, oracle, kernel):
+    """Gillespie::advance_one_reaction (src/gillespie.rs:270-297) for every trajectory: after k calls time, species and
+    event count equal k single steps of the oracle; an absorbing state gives t = +inf."""
+    model = models.sir()
+    arith = 1 if kernel == "prebuilt" else 0
+    net = models.build_network(model, arith)
+    n = 40
+    seeds = numpy_seeds(n, rng=31)
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds, kernel={"table": 1, "nvrtc": 2, "prebuilt": 3}[kernel])
+    onet = oracle_network(oracle, model, arith)
+    for k in (1, 2, 7):
+        b.set_species(model["x0"])
+        b.set_time(0.0)
+        b.seed(seeds)
+        for _ in range(k):
+            b.advance_one_reaction()
+        t, x = b.times(), b.species()
+        for i in range(n):
+            rt, rx, _ = onet.step_one(model["x0"], int(seeds[i]), k)
+            assert t[i] == rt and x[i].tolist() == rx.tolist(), (k, i)
+    # nothing can happen: t = +inf, no random word used
+    b2 = ffi.Batch(net, 8, [10, 0, 0], seeds=models.seeds_sequence(8), kernel={"table": 1, "nvrtc": 2, "prebuilt": 3}[kernel])
+    b2.advance_one_reaction()
+    assert np.isinf(b2.times()).all() and (b2.species() == [10, 0, 0]).all()
+    b.close()
+    b2.close()
+
+
+@pytest.mark.parametrize("schedule", [1, 2])
+def test_more_than_65535_sample_rows(gpu, ffi, schedule):
+    """(nb_steps + 1) * n_save beyond the 65535 limit of a grid's y dimension: samples and row sums."""
+    model = models.sir()
+    net = models.build_network(model)
+    n = 40
+    b = ffi.Batch(net, n, model["x0"], seeds=models.seeds_sequence(n, 2))
+    b.set_schedule(schedule)
+    b.run_grid(250.0, 70_000, save_idx=[1])
+    out = b.samples().astype(np.int64)
+    assert out.shape == (70_001, 1, n)
+    s1, s2 = b.sample_sums()
+    np.testing.assert_array_equal(s1, out.sum(axis=2).ravel())
+    np.testing.assert_array_equal(s2.astype(np.int64), (out * out).sum(axis=2).ravel())
+    b.close()
+
+
+def test_table_kernel_batches_with_different_networks_run_side_by_side(gpu, ffi, oracle):
+    """Two host threads, two batches on the same device, two different networks on the table-driven kernel: the
+    network travels with the batch (no process-global table), so neither run disturbs the other."""
+    import threading
+    ma, mb = models.sir(), models.dimers()
+    na, nb = 20_000, 600
+    sa, sb = models.seeds_sequence(na, 1), models.seeds_sequence(nb, 2)
+    ra, _, _ = oracle_network(oracle, ma).run_batch(ma["x0"], sa, 250.0, 25, threads=8)
+    rb, _, _ = oracle_network(oracle, mb).run_batch(mb["x0"], sb, 0.3, 3, threads=8)
+    results = {}
+
+    def work(key, model, seeds, tmax, nbs, reps):
+        net = models.build_network(model)
+        outs = []
+        for _ in range(reps):
+            b = ffi.Batch(net, len(seeds), model["x0"], seeds=seeds, kernel=1)
+            b.run_grid(tmax, nbs)
+            outs.append(b.samples())
+            b.close()
+        results[key] = outs
+
+    ta = threading.Thread(target=work, args=("a", ma, sa, 250.0, 25, 6))
+    tb = threading.Thread(target=work, args=("b", mb, sb, 0.3, 3, 6))
+    ta.start(); tb.start(); ta.join(); tb.join()
+    for o in results["a"]:
+        np.testing.assert_array_equal(o, ra)
+    for o in results["b"]:
+        np.testing.assert_array_equal(o, rb)
+
+
+def test_launches_on_a_caller_stream_do_not_block(gpu, ffi, oracle):
+    """On a caller-owned stream run_grid returns before the device is done; rebop_batch_synchronize reports status and
+    events, and the samples are those of a blocking run."""
+    import torch
+    model = models.dimers()
+    net = models.build_network(model, 1)
+    n = 4000
+    seeds = models.seeds_sequence(n, first=4)
+    ref, _, tot = oracle_network(oracle, model, 1).run_batch(model["x0"], seeds, 0.2, 4, threads=8)
+    stream = torch.cuda.Stream()
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds)
+    b.set_stream(stream.cuda_stream)
+    host = ffi.PinnedBuffer((5, 4, n), np.int32)
+    b.run_grid(0.2, 4, host_out=host.array)
+    b.synchronize()
+    np.testing.assert_array_equal(host.array, ref)
+    assert b.events() == (tot, tot)
+    b.set_max_iters(16)
+    b.set_species(model["x0"])
+    b.set_time(0.0)
+    b.seed(seeds)
+    b.run_grid(0.2, 4)  # returns at once; the cap is reported by synchronize
+    with pytest.raises(ffi.RebopError) as e:
+        b.synchronize()
+    assert e.value.status == ffi.ERR_ITER_CAP
+    b.set_stream(None)
+    b.close()
+    host.close()
+
+
+def test_ensemble_handle_matches_single_batch(gpu, ffi, oracle):
+    """rebop_ensemble_* over every visible device: samples, exact sums and the device-finalised mean / variance equal
+    those of one batch on one device (and the oracle), whatever the device count."""
+    from rebop_b200 import ensemble as ens
+    model = models.sir()
+    net = models.build_network(model)
+    n = 10_001
+    seeds = models.seeds_sequence(n, first=50)
+    ref, _, tot = oracle_network(oracle, model).run_batch(model["x0"], seeds, 250.0, 20, threads=8)
+    devices = list(range(ffi.device_count()))
+    e = ffi.Ensemble(net, n, model["x0"], devices, seeds=seeds)
+    assert sum(c for _, _, c in e.shards()) == n
+    host = np.empty((21, 3, n), dtype=np.int32)
+    e.run_grid(250.0, 20, host_out=host)
+    np.testing.assert_array_equal(host, ref)
+    np.testing.assert_array_equal(e.samples(), ref)
+    assert e.events()[1] == tot
+    s1, s2 = e.sums()
+    r64 = ref.astype(np.int64)
+    np.testing.assert_array_equal(s1.reshape(21, 3), r64.sum(axis=2))
+    np.testing.assert_array_equal(s2.reshape(21, 3).astype(np.int64), (r64 * r64).sum(axis=2))
+    mean, var = e.stats()
+    m2, v2 = ens.finalize_stats(s1, s2, n)
+    np.testing.assert_allclose(mean.ravel(), m2, rtol=1e-15, atol=0)
+    np.testing.assert_allclose(var.ravel(), v2, rtol=1e-14, atol=0)
+    e.close()
+
+
+def test_ensemble_over_two_devices_is_bit_identical(gpu, ffi):
+    """Needs two physical GPUs (skipped otherwise): 1-device and 2-device ensembles give the same samples and the same
+    NCCL-all-reduced sums bit for bit."""
+    if ffi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    model = models.dimers()
+    net = models.build_network(model, 1)
+    n = 50_001
+    one = ffi.Ensemble(net, n, model["x0"], [0], seed_base=7)
+    two = ffi.Ensemble(net, n, model["x0"], [0, 1], seed_base=7)
+    one.run_grid(0.2, 4)
+    two.run_grid(0.2, 4)
+    np.testing.assert_array_equal(one.samples(), two.samples())
+    a1, a2 = one.sums()
+    b1, b2 = two.sums()
+    np.testing.assert_array_equal(a1, b1)
+    np.testing.assert_array_equal(a2, b2)
+    m1, v1 = one.stats()
+    m2, v2 = two.stats()
+    np.testing.assert_array_equal(m1, m2)
+    np.testing.assert_array_equal(v1, v2)
+    assert one.events() == two.events()
+    one.close()
+    two.close()

@@ -54,7 +54,7 @@ def test_rate_expressions_and_lowering(ffi):
     np.testing.assert_array_equal(s.rates([3.0, 0.5]), [2.0 * 3.0 / (0.5 + 1.0) - 1e-3, -0.5])
     src = s.network([3.0, 0.5]).codegen()
     # macro arithmetic: integer falling factorial of the `2 A` term, then B; jump (-2, +2) packed as 0x02fe
-    assert "define_system! arithmetic" in src and "__dmul_rn(d0, __dsub_rn(d0, 1.0))" in src and "0x000002fe" in src
+    assert "define_system! arithmetic" in src and "__dmul_rn(d0, __dsub_rn(d0, 1.0))" in src and "0x000102fe" in src  # -2, +2, event-count lane
 
 
 def test_with_parameters_arity():
@@ -201,7 +201,7 @@ def test_parameters_can_change_between_calls(gpu, ffi, oracle):
 
 def test_sysgen_tool_and_nvcc_cross_compile(tmp_path):
     """The build.rs analogue end to end, without a GPU: DSL text -> rebop_sysgen -> nvcc (sm_100a) -> an object
-    with the four entry points (time grid static/dynamic, event log count/write) and the registration."""
+    with the five entry points (time grid in its three schedules, event log count/write) and the registration."""
     import shutil
     import subprocess
     csrc = os.path.join(ROOT, "rebop_b200", "csrc")
@@ -216,14 +216,14 @@ def test_sysgen_tool_and_nvcc_cross_compile(tmp_path):
     cu = tmp_path / "schloegl.cu"
     subprocess.check_call([tool, str(rsys), "-o", str(cu)])
     text = cu.read_text(encoding="utf-8")
-    for suffix in ("", "_dyn", "_evc", "_evw"):
+    for suffix in ("", "_dyn", "_dns", "_evc", "_evw"):
         assert f"rb_ssa_sys_Schloegl{suffix}(const __grid_constant__ SsaRunParams p)" in text
     assert "rb_register_prebuilt" in text
     obj = tmp_path / "schloegl.o"
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
                            "-Xcompiler", "-fPIC", "-I", csrc, "-c", str(cu), "-o", str(obj)])
     sass = subprocess.check_output(["cuobjdump", "-sass", str(obj)], text=True)
-    assert sass.count("Function : rb_ssa_sys_Schloegl") == 4
+    assert sass.count("Function : rb_ssa_sys_Schloegl") == 5
     assert "DFMA" in sass and "IDP.4A" in sass  # IEEE divide and packed stoichiometry update are in there
     # a malformed system is refused with the parser's message
     bad = tmp_path / "bad.rsys"
