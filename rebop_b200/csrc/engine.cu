@@ -997,7 +997,8 @@ static int run_grid_impl(rebop_batch* b, double tmax, uint32_t nb_steps, const u
       lane_slots += b->lane_slots_last;
       read_times(b, n_save != 0, &ms, &finish_ms);
     }
-    if (st == REBOP_OK && host_out && n_save && !is_async(b))
+    if (st) break;  // (before ++sgm: a segment cut short by the watchdog is the one the repeated call continues)
+    if (host_out && n_save && !is_async(b))
       st = copy_rows_to_host(b, host_out, host_ld, (size_t)first * n_save, (size_t)(last - first + 1) * n_save,
                              overlap ? b->copy_stream : b->stream);
   }
