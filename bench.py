@@ -20,8 +20,17 @@ t = 200 in ONE kernel launch, samples left in HBM as int32 [step][species][traje
   cpu_baseline  the oracle's define_system!-style straight-line Vilar code on all host cores, on a
          bounded sample of the same workload (N=1, rank 0 only).
 
+  parity_check  inside the same run: the first 256 trajectories of the last end-to-end step (host buffer)
+         are recomputed by the oracle from the same seeds and compared bit for bit; a mismatch makes the
+         run exit non-zero, so a printed number always belongs to a checked result.
+  configs  the other BASELINE.json configurations, each in its stated form, as short runs (1 warm-up + 3
+         steps): C1 SIR through the function API arithmetic, C2 Dimers in define_system! arithmetic, C3
+         Michaelis-Menten with an expression rate through the Python `Gillespie.run` (trajectories/s, full
+         samples and reduce=True), C5 the synthetic 100 x 500 network, 10^6 trajectories sharded over the GPUs.
+
 `--impl reference` times the reference's CPU algorithm (the oracle port; the Rust crate cannot be
-compiled in this image) on the host cores and prints the same JSON line shape.
+compiled in this image) on the host cores and prints the same JSON line shape.  It does not import the
+product package (no CUDA library is mapped into that process).
 """
 from __future__ import annotations
 
@@ -38,6 +47,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
+
+
+
+def load_models():
+    """rebop_b200/models.py as a stand-alone module: plain data, no import of the package (whose __init__ loads the
+    CUDA library)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("rebop_b200_models_data", os.path.join(ROOT, "rebop_b200", "models.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
 
 METRIC = "ssa_reaction_events_per_sec"
 UNIT = "events/s"
@@ -63,7 +85,9 @@ def host_cores() -> int:
 def workload_config(args, n_gpus):
     return {
         "workload": f"{args.model} ensemble, define_system! arithmetic, tmax={args.tmax:g}, nb_steps={args.nb_steps}, "
-                    f"{args.traj_per_gpu} trajectories per GPU ({args.traj_per_gpu * n_gpus} total), all species saved",
+                    f"{args.traj_per_gpu} trajectories per GPU ({args.traj_per_gpu * n_gpus} total), all species saved "
+                    f"(--impl reference times a bounded sample of this workload per step on the host cores: its size is in "
+                    f"`sample` and `cpu_baseline.sample` of that line)",
         "trajectories_per_gpu": args.traj_per_gpu,
         "trajectories_total": args.traj_per_gpu * n_gpus,
         "tmax": args.tmax,
@@ -113,11 +137,14 @@ def run_reference(args, model):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
+        "sample": sample, "trajectories_per_step": per_step,
         "trajectories_per_s": per_step * args.steps / dt,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "oracle port of the reference's define_system! code path (the Rust crate cannot be built here: no cargo/rustc)",
+        "note": "oracle port of the reference's define_system! code path (the Rust crate cannot be built here: no cargo/rustc); "
+                "built with gcc -O3 -ffp-contract=off, without -march=native (the .so travels from the build container to a "
+                "different host: oracle/Makefile)",
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -203,6 +230,196 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+def oracle_samples(model, arith, seeds, tmax, nb_steps, threads, save_idx=None):
+    """The checker: oracle samples [nb_steps+1][n_save][len(seeds)] for a model dict in the given arithmetic."""
+    from oracle import oracle as O  # checker only
+
+    if arith == 1 and save_idx is None:
+        try:
+            return O.run_batch_macro(model["name"], model["params"], model["x0"], seeds, tmax, nb_steps, threads=threads,
+                                     want_events=False)[0]
+        except KeyError:
+            pass
+    net = O.Network(len(model["species"]), [("lma", k, terms, diff) for k, terms, diff in model["reactions"]], arith=arith)
+    return net.run_batch(model["x0"], seeds, tmax, nb_steps, save_idx=save_idx, threads=threads, want_events=False)[0]
+
+
+def oracle_parity(model, arith, seeds, tmax, nb_steps, got, threads, save_idx=None):
+    """Compare `got` [nb_steps+1][n_save][len(seeds)] with the oracle on the same seeds, bit for bit."""
+    t0 = time.perf_counter()
+    ref = oracle_samples(model, arith, seeds, tmax, nb_steps, threads, save_idx)
+    equal = bool(np.array_equal(np.asarray(got).astype(np.int64), ref.astype(np.int64)))
+    return {"n": int(len(seeds)), "equal": equal, "rows": int(ref.shape[0] * ref.shape[1]),
+            "oracle_seconds": round(time.perf_counter() - t0, 3),
+            "what": "samples of the first trajectories of the last timed end-to-end step vs the CPU oracle on the same seeds"}
+
+
+class _HostBuffer:
+    """Page-locked host array when the box grants it, pageable otherwise (stated in the line)."""
+
+    def __init__(self, ffi, shape, dtype):
+        self.kind = "pinned"
+        try:
+            self._pin = ffi.PinnedBuffer(shape, dtype)
+            self.array = self._pin.array
+        except ffi.RebopError:
+            self._pin = None
+            self.array = np.empty(shape, dtype=dtype)
+            self.kind = "pageable (page-locking the buffer failed)"
+
+    def close(self):
+        self.array = None
+        if self._pin is not None:
+            self._pin.close()
+
+
+def bench_config(tag, model, arith, n, sample_dtype, ctx, steps, warmup, save_idx=None, parity_n=64, scaling="weak"):
+    """One BASELINE configuration as a short run on this rank's GPU: device-resident and end-to-end through the C ABI
+    (host buffers in the timed region), FP64-issue roofline fraction, lane efficiency and an oracle check of the first
+    trajectories of the last end-to-end step.  ctx: rank/world/local, reducers, ffi/models modules, fp64 peak."""
+    _ffi, models = ctx["ffi"], ctx["models"]
+    rank, world, local = ctx["rank"], ctx["world"], ctx["local"]
+    S = len(model["species"])
+    n_save = S if save_idx is None else len(save_idx)
+    nb, tmax = model["nb_steps"], model["tmax"]
+    net = models.build_network(model, arith)
+    dtype = np.dtype(sample_dtype)
+
+    def base(i):
+        return (i * world + rank) * n
+
+    b = _ffi.Batch(net, n, model["x0"], seeds=None, seed_base=base(0), device=local)
+    b.set_sample_dtype(dtype)
+    x0 = np.asarray(model["x0"], dtype=np.int64)
+
+    def dev_step(i):
+        b.set_species(x0)
+        b.set_time(0.0)
+        b.seed(None, base(i))
+        b.run_grid(tmax, nb, save_idx=save_idx)
+        return b.events()[1], b.last_kernel_ms, b.last_finish_ms, b.lane_slots
+
+    for i in range(warmup):
+        dev_step(i)
+    ctx["barrier"]()
+    events = loop_ms = fin_ms = slots = 0
+    w0 = time.perf_counter()
+    for i in range(steps):
+        ev, ms, fm, sl = dev_step(warmup + i)
+        events += ev; loop_ms += ms; fin_ms += fm; slots += sl
+    ctx["barrier"]()
+    wall_dev = ctx["max"](time.perf_counter() - w0)
+    dev_ms = ctx["max"](loop_ms + fin_ms)  # device time of the kernels (ensemble loop + sample finishing), max over ranks
+    tot_events = ctx["sum"](float(events))
+    kernel_used, schedule_used = b.kernel_used, b.schedule_used
+
+    # end to end: seeds and x0 from host memory, samples into a host buffer, all inside the timed region
+    host_seeds = _HostBuffer(_ffi, (n,), np.uint64)
+    host_out = _HostBuffer(_ffi, (nb + 1, n_save, n), dtype)
+
+    def e2e_step(i):
+        host_seeds.array[:] = np.arange(base(i), base(i) + n, dtype=np.uint64)
+        b.set_species(x0)
+        b.set_time(0.0)
+        b.seed(host_seeds.array)
+        b.run_grid(tmax, nb, save_idx=save_idx, host_out=host_out.array)
+        return b.events()[1]
+
+    for i in range(warmup):
+        e2e_step(i)
+    ctx["barrier"]()
+    w0 = time.perf_counter()
+    e2e_events = 0
+    for i in range(steps):
+        e2e_events += e2e_step(warmup + i)
+    ctx["barrier"]()
+    e2e_s = ctx["max"](time.perf_counter() - w0)
+    e2e_total = ctx["sum"](float(e2e_events))
+    last = warmup + steps - 1
+    n_chk = min(parity_n, n)
+    parity = oracle_parity(model, arith, np.arange(base(last), base(last) + n_chk, dtype=np.uint64), tmax, nb,
+                           host_out.array[:, :, :n_chk], host_cores(), save_idx)
+    parity["equal"] = bool(ctx["min"](1.0 if parity["equal"] else 0.0) == 1.0)
+    host_mem = host_out.kind
+    host_out.close()
+    host_seeds.close()
+    b.close()
+    F = fp64_ops_per_event(model)
+    achieved = events * F / (loop_ms * 1e-3)
+    return {
+        "workload": f"{tag}: {model['name']}, {'define_system!' if arith == 1 else 'function-API'} arithmetic, tmax={tmax:g}, "
+                    f"nb_steps={nb}, {n} trajectories per GPU x {world} GPU(s), {n_save} of {S} species saved as {dtype.name}",
+        "value": tot_events / (dev_ms * 1e-3), "unit": UNIT, "scaling": scaling,
+        "ms_per_step": dev_ms / steps, "loop_ms_per_step": loop_ms / steps, "finish_ms_per_step": fin_ms / steps,
+        "wall_ms_per_step": wall_dev / steps * 1e3,
+        "trajectories_per_s": n * world * steps / (dev_ms * 1e-3),
+        "e2e": {"value": e2e_total / e2e_s, "unit": UNIT, "ms_per_step": e2e_s / steps * 1e3,
+                "trajectories_per_s": n * world * steps / e2e_s, "h2d_bytes_per_step": int(n * 8 + S * 8),
+                "d2h_bytes_per_step": int((nb + 1) * n_save * n * dtype.itemsize), "host_memory": host_mem},
+        "frac": achieved / ctx["fp64_peak"], "ops_per_event": F, "lane_efficiency": events / slots if slots else None,
+        "events_per_trajectory": events / (n * steps), "kernel": kernel_used, "schedule": schedule_used, "steps": steps,
+        "warmup": warmup, "parity_check": parity,
+    }
+
+
+def bench_python_mm(n, ctx, steps, warmup):
+    """BASELINE config 3: examples/mm.py of the reference (expression rate V * A / (Km + A)) as a batched
+    `Gillespie.run` through the Python binding: trajectories/s end to end, with the samples returned to the caller
+    (int16, the narrowest type the binding offers; counts are <= 100) and with reduce=True (mean/variance only)."""
+    import rebop_b200
+
+    rank, world, local = ctx["rank"], ctx["world"], ctx["local"]
+    mm = rebop_b200.Gillespie()
+    mm.add_reaction("V * A / (Km + A)", ["A"], ["P"])
+    kw = dict(tmax=250, nb_steps=100, params={"V": 1, "Km": 20}, n_trajectories=n, device=local)
+
+    def timed(**extra):
+        for i in range(warmup):
+            mm.run({"A": 100}, rng=1000 * rank + i, **kw, **extra)
+        ctx["barrier"]()
+        t0 = time.perf_counter()
+        events = kernel_ms = 0
+        ds = None
+        for i in range(steps):
+            ds = mm.run({"A": 100}, rng=1000 * rank + warmup + i, **kw, **extra)
+            events += mm.last_events
+            kernel_ms += mm.last_kernel_ms
+        ctx["barrier"]()
+        dt = ctx["max"](time.perf_counter() - t0)
+        return ds, dt, ctx["sum"](float(events)), kernel_ms
+
+    ds, dt, events, kernel_ms = timed(dtype=np.int16)
+    # parity of the last returned samples: the same seeds through the oracle's expression engine
+    from oracle import oracle as O  # checker only
+
+    n_chk = min(64, n)
+    seeds = np.random.default_rng(1000 * rank + warmup + steps - 1).integers(np.iinfo(np.uint64).max, size=n, dtype=np.uint64)[:n_chk]
+    # V * A / (Km + A) with V = 1, Km = 20, post-order as Expr::eval walks it (src/expr.rs:24-38)
+    prog = [("const", 0, 1.0), ("species", 0, 0), ("mul", 0, 0), ("const", 0, 20.0), ("species", 0, 0), ("add", 0, 0),
+            ("div", 0, 0)]
+    try:
+        ref = O.Network(2, [("expr", prog, [-1, 1])]).run_batch([100, 0], seeds, 250.0, 100, threads=host_cores(),
+                                                               want_events=False)[0]
+        got = np.stack([np.asarray(ds["A"])[:, :n_chk], np.asarray(ds["P"])[:, :n_chk]], axis=1)
+        equal = bool(np.array_equal(got.astype(np.int64), ref.astype(np.int64)))
+    except Exception as e:  # noqa: BLE001 - a failing checker is reported, it does not hide the measurement
+        equal = f"checker error: {e}"
+    if isinstance(equal, bool):
+        equal = bool(ctx["min"](1.0 if equal else 0.0) == 1.0)
+    _, dt_r, _, kernel_ms_r = timed(reduce=True)
+    return {
+        "workload": f"C3: Michaelis-Menten A -> P at rate 'V * A / (Km + A)' (examples/mm.py), rebop_b200.Gillespie.run("
+                    f"n_trajectories={n}) per GPU x {world} GPU(s), tmax=250, nb_steps=100, both species returned as int16",
+        "value": n * world * steps / dt, "unit": "trajectories/s", "events_per_s": events / dt,
+        "ms_per_call": dt / steps * 1e3, "kernel_ms_per_call": kernel_ms / steps,
+        "d2h_bytes_per_call": int(101 * 2 * n * 2),
+        "reduce": {"value": n * world * steps / dt_r, "unit": "trajectories/s", "ms_per_call": dt_r / steps * 1e3,
+                   "kernel_ms_per_call": kernel_ms_r / steps,
+                   "what": "reduce=True: ensemble mean and variance per sample time, samples never leave the GPU"},
+        "steps": steps, "warmup": warmup, "parity_check": {"n": n_chk, "equal": equal},
+    }
+
+
 def run_gpu(args, model):
     import torch
     import torch.distributed as dist
@@ -239,10 +456,18 @@ def run_gpu(args, model):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def min_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
     n = args.traj_per_gpu
     S = len(model["species"])
     nb = args.nb_steps
-    net = models.build_network(model, _ffi.ARITH_MACRO)
+    arith = _ffi.ARITH_MACRO  # BASELINE config 4: the Vilar oscillator through define_system!
+    net = models.build_network(model, arith)
     kernel = {"auto": _ffi.KERNEL_AUTO, "table": _ffi.KERNEL_TABLE, "nvrtc": _ffi.KERNEL_NVRTC,
               "prebuilt": _ffi.KERNEL_PREBUILT}[args.kernel]
 
@@ -304,6 +529,7 @@ def run_gpu(args, model):
 
     # ---- e2e: host buffers through the C ABI ---------------------------------------------
     e2e = None
+    parity = None
     if not args.no_e2e:
         host_seeds = _ffi.PinnedBuffer((n,), np.uint64)
         host_memory = "pinned"
@@ -344,6 +570,13 @@ def run_gpu(args, model):
         e2e_s = max_over_ranks(time.perf_counter() - w0)
         e2e_total = sum_over_ranks(float(e2e_events))
         checksum = int(host_out.array[-1].astype(np.int64).sum())
+        # ---- parity of the very result that was timed: the oracle recomputes the first trajectories of the last step
+        n_chk = min(args.parity_n, n)
+        if n_chk:
+            last = args.warmup + args.steps - 1
+            chk_seeds = np.arange(shard_base(last), shard_base(last) + n_chk, dtype=np.uint64)
+            parity = oracle_parity(model, arith, chk_seeds, args.tmax, nb, host_out.array[:, :, :n_chk], host_cores())
+            parity["equal"] = bool(min_over_ranks(1.0 if parity["equal"] else 0.0) == 1.0)  # every rank checks its own shard
         e2e = {"value": e2e_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 8 + S * 4),
                "d2h_bytes_per_step": int((nb + 1) * S * n * 4), "ms_per_step": e2e_s / args.steps * 1e3,
                "kernel_ms_per_step": float(np.mean(e2e_kernel_ms[-args.steps:])),
@@ -400,6 +633,28 @@ def run_gpu(args, model):
                "sample": f"{n_cpu} trajectories of the same workload in {dt:.1f} s (oracle, define_system! form, {cores} threads)"}
 
     batch.close()
+
+    # ---- the other BASELINE configurations, each in its stated form (short runs)
+    configs = None
+    if not args.no_configs:
+        ctx = {"ffi": _ffi, "models": models, "rank": rank, "world": world, "local": local, "barrier": barrier,
+               "max": max_over_ranks, "sum": sum_over_ranks, "min": min_over_ranks, "fp64_peak": fp64_peak}
+        cs, cw = args.config_steps, args.config_warmup
+        n1 = args.config_traj
+        configs = {
+            # C1: SIR through the Gillespie function API (its arithmetic, its reaction choice), counts <= 1000 -> int16
+            "C1_sir_api": bench_config("C1", models.sir(), _ffi.ARITH_API, n1, np.int16, ctx, cs, cw),
+            # C2: Dimers as define_system! writes it, final state only (nb_steps = 1)
+            "C2_dimers_macro": bench_config("C2", models.dimers(), _ffi.ARITH_MACRO, n1, np.int32, ctx, cs, cw),
+            # C3: Python binding, expression rate, 10^7 trajectories (split over the GPUs of the run)
+            "C3_mm_python": bench_python_mm(max(1, args.config_traj_mm // world), ctx, cs, cw),
+            # C5: synthetic 100 x 500 network, function-API arithmetic, 10^6 trajectories sharded over the GPUs (strong
+            # scaling); the first 10 species are returned (all 100 would be 40 GB of int32 per step)
+            "C5_synthetic_api": bench_config("C5", models.synthetic(), _ffi.ARITH_API, max(1, n1 // world), np.int32, ctx, cs, cw,
+                                             save_idx=list(range(10)), parity_n=16, scaling="strong"),
+        }
+    all_equal = all(v is True for v in [parity and parity["equal"]] +
+                    [c["parity_check"]["equal"] for c in (configs or {}).values()] if v is not None)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -410,12 +665,16 @@ def run_gpu(args, model):
             "wall_ms_per_step": wall / args.steps * 1e3,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "kernel": roofline["kernel"], "roofline": roofline, "cpu_baseline": cpu,
+            "parity_check": parity, "configs": configs,
             "ensemble_stats": {"ms": stats_ms, "collective": "nccl all_reduce(int64 sum)" if world > 1 else "none (1 GPU)",
                                "mean_at_tmax": dict(zip(model["species"], mean_last))},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not all_equal:
+        print("bench.py: PARITY CHECK FAILED: the timed result differs from the oracle", file=sys.stderr)
+        return 3
     return 0
 
 
@@ -432,6 +691,12 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "table", "nvrtc", "prebuilt"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configurations")
+    ap.add_argument("--parity-n", type=int, default=256, help="trajectories of the last e2e step recomputed by the oracle")
+    ap.add_argument("--config-steps", type=int, default=3)
+    ap.add_argument("--config-warmup", type=int, default=1)
+    ap.add_argument("--config-traj", type=int, default=1_000_000, help="trajectories of C1/C2 per GPU and of C5 in total")
+    ap.add_argument("--config-traj-mm", type=int, default=10_000_000, help="trajectories of C3 in total")
     ap.add_argument("--cpu-traj-per-core", type=int, default=1024, help="cpu_baseline sample size per host core")
     ap.add_argument("--ref-traj-per-core", type=int, default=512, help="--impl reference: trajectories per core per step")
     args = ap.parse_args()
@@ -439,7 +704,7 @@ def main():
     if not os.path.exists(os.path.join(ROOT, "rebop_b200", "librebop_b200.so")) and int(os.environ.get("LOCAL_RANK", "0")) == 0:
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "rebop_b200", "csrc"), "-j8"], stdout=sys.stderr)
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=sys.stderr)
-    from rebop_b200 import models
+    models = load_models()  # plain data; the product package (and its CUDA library) is imported by the GPU arm only
     model = models.MODELS[args.model]()
     args.tmax = model["tmax"] if args.tmax is None else args.tmax
     args.nb_steps = model["nb_steps"] if args.nb_steps is None else args.nb_steps

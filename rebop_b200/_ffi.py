@@ -20,7 +20,7 @@ SAMPLES_I16, SAMPLES_I32, SAMPLES_I64 = 2, 4, 8
 SAMPLE_DTYPES = {2: np.int16, 4: np.int32, 8: np.int64}
 SCHEDULE_AUTO, SCHEDULE_STATIC, SCHEDULE_SPARSE, SCHEDULE_DENSE = 0, 1, 2, 3
 ARITH_API, ARITH_MACRO = 0, 1
-KERNEL_AUTO, KERNEL_TABLE, KERNEL_NVRTC, KERNEL_PREBUILT = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_TABLE, KERNEL_NVRTC, KERNEL_PREBUILT, KERNEL_PDM = 0, 1, 2, 3, 4
 OPCODES = dict(const=0, species=1, neg=2, add=3, sub=4, mul=5, div=6, pow=7, max=8, min=9, exp=10)
 
 

@@ -263,6 +263,23 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   o << "#define RB_TICK " << tick << "u\n";
   if (unroll != 1) o << "#define RB_INNER_UNROLL " << unroll << "\n";
   if (conv == 1) o << "#define RB_STATE_INT\n";
+  if (const char* env = std::getenv("REBOP_B200_CODEGEN")) {  // defs=RB_A+RB_B: experimental switches of ssa_kernel.cuh
+    const std::string e(env);
+    const size_t pos = e.find("defs=");
+    if (pos != std::string::npos) {
+      std::string list = e.substr(pos + 5, e.find(',', pos) == std::string::npos ? std::string::npos : e.find(',', pos) - pos - 5);
+      size_t a = 0;
+      while (a < list.size()) {
+        size_t b = list.find('+', a);
+        if (b == std::string::npos) b = list.size();
+        std::string d = list.substr(a, b - a);
+        const size_t eq = d.find(':');
+        if (eq != std::string::npos) d[eq] = ' ';
+        if (!d.empty()) o << "#define " << d << "\n";
+        a = b + 1;
+      }
+    }
+  }
   o << "#include \"ssa_kernel.cuh\"\n\n";
 
   // packed stoichiometry table

@@ -22,7 +22,8 @@ from rebop_b200.dataset import make_dataset
 
 __all__ = ("Gillespie",)
 
-_KERNELS = {"auto": _ffi.KERNEL_AUTO, "table": _ffi.KERNEL_TABLE, "nvrtc": _ffi.KERNEL_NVRTC}
+_KERNELS = {"auto": _ffi.KERNEL_AUTO, "table": _ffi.KERNEL_TABLE, "nvrtc": _ffi.KERNEL_NVRTC, "prebuilt": _ffi.KERNEL_PREBUILT,
+            "fast": _ffi.KERNEL_PDM}
 _U64_MAX = np.iinfo(np.uint64).max
 
 
