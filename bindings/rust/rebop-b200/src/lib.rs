@@ -256,3 +256,70 @@ impl Drop for SystemBatch {
         }
     }
 }
+
+/// `define_system!` for GPU ensembles, with the grammar of rebop's macro (`src/gillespie_macro.rs:49-61`):
+///
+/// ```ignore
+/// rebop_b200::define_system! {
+///     r1 r2;
+///     SIR { S, I, R }
+///     r_infection: S + I  => I + I    @ r1
+///     r_remission: I      => R        @ r2
+/// }
+/// let mut sir = SIR::with_parameters(1e-4, 0.01);
+/// sir.S = 999;
+/// sir.I = 1;
+/// let mut ensemble = sir.ensemble(1_000_000, 0, 0)?;   // trajectory i is rebop's SIR seeded with i
+/// ensemble.advance_until(250.0)?;
+/// ```
+///
+/// rebop expands the system into straight-line Rust; here the text of the invocation is the system (the engine parses
+/// the same grammar, `rebop_system_parse`), and the network-specialised CUDA kernel for it is compiled at build time
+/// when the same text sits in `rebop-b200-sys/systems/<name>.rsys` (see that crate's `build.rs`: rebop_sysgen + nvcc),
+/// or by NVRTC on first use otherwise.  The generated struct has the fields of rebop's (`src/gillespie_macro.rs:62-71`):
+/// one `isize` per species -- the initial count of every trajectory -- and one `f64` per parameter.
+#[macro_export]
+macro_rules! define_system {
+    ($($tt:tt)*) => {
+        $crate::__define_system_impl! { text = { stringify!($($tt)*) }; $($tt)* }
+    };
+}
+
+#[doc(hidden)]
+#[macro_export]
+macro_rules! __define_system_impl {
+    (
+      text = { $text:expr };
+      $($param:ident)*;
+      $name:ident { $($species:ident),* }
+      $($rname:ident:
+          $($($nr:literal)? $r:ident)? $(+ $($tnr:literal)? $tr:ident)* =>
+          $($($np:literal)? $p:ident)? $(+ $($tnp:literal)? $tp:ident)*
+          @ $rate:expr)*
+    ) => {
+        #[allow(non_snake_case)]
+        #[derive(Clone, Debug)]
+        struct $name {
+            $(pub $species: isize,)*
+            $(pub $param: f64,)*
+        }
+        #[allow(non_snake_case, dead_code)]
+        impl $name {
+            /// The text of the invocation: what the engine parses and what the build-time kernel is keyed by.
+            pub const TEXT: &'static str = $text;
+            /// `Name::new()` (`src/gillespie_macro.rs:75-82`): species 0, parameters NaN.
+            fn new() -> Self {
+                $name { $($species: 0,)* $($param: f64::NAN,)* }
+            }
+            /// `Name::with_parameters(..)` (`src/gillespie_macro.rs:91-98`).
+            fn with_parameters($($param: f64),*) -> Self {
+                $name { $($species: 0,)* $($param,)* }
+            }
+            /// `n` copies of this problem resident on GPU `device`; trajectory i is seeded with `seed + i`
+            /// (`seed(u64)`, `src/gillespie_macro.rs:84-88`).
+            fn ensemble(&self, n: usize, seed: u64, device: i32) -> Result<$crate::SystemBatch, $crate::Error> {
+                $crate::SystemBatch::new(Self::TEXT, &[$(self.$param),*], &[$(self.$species as i64),*], n, seed, device)
+            }
+        }
+    };
+}

@@ -118,6 +118,10 @@ int rebop_network_nb_reactions(const rebop_network* net, uint32_t* out); /* src/
  * in bytes (the source includes its NUL terminator). */
 int rebop_network_codegen(const rebop_network* net, char* buf, size_t cap, size_t* needed);
 int rebop_network_jit_cubin(const rebop_network* net, char* buf, size_t cap, size_t* needed);
+/* The same two for the partial-propensity kernel (REBOP_KERNEL_PDM, see rebop_batch_set_kernel): REBOP_ERR_LIMIT with
+ * the reason when the network is not elementary mass action. */
+int rebop_network_codegen_pdm(const rebop_network* net, char* buf, size_t cap, size_t* needed);
+int rebop_network_jit_cubin_pdm(const rebop_network* net, char* buf, size_t cap, size_t* needed);
 
 /* ---- define_system! (src/gillespie_macro.rs:49-129) ---- */
 

@@ -69,6 +69,8 @@ SIGNATURES = {
     "rebop_network_nb_reactions": (C.c_int, [_vp, _u32p]),
     "rebop_network_codegen": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
     "rebop_network_jit_cubin": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_network_codegen_pdm": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
+    "rebop_network_jit_cubin_pdm": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
     "rebop_system_parse": (C.c_int, [C.c_char_p, _pp]),
     "rebop_system_destroy": (None, [_vp]),
     "rebop_system_name": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _szp]),
@@ -281,6 +283,21 @@ class Network:
         buf = C.create_string_buffer(need.value)
         check(lib.rebop_network_codegen(self._h, buf, need.value, None))
         return buf.value.decode("utf-8")
+
+    def codegen_pdm(self) -> str:
+        """Source of the partial-propensity kernel (KERNEL_PDM) for this network."""
+        need = C.c_size_t()
+        check(lib.rebop_network_codegen_pdm(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(lib.rebop_network_codegen_pdm(self._h, buf, need.value, None))
+        return buf.value.decode()
+
+    def jit_cubin_pdm(self) -> bytes:
+        need = C.c_size_t()
+        check(lib.rebop_network_jit_cubin_pdm(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(lib.rebop_network_jit_cubin_pdm(self._h, buf, need.value, None))
+        return buf.raw[:need.value]
 
     def jit_cubin(self) -> bytes:
         need = C.c_size_t()

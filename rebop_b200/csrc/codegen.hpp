@@ -36,3 +36,9 @@ bool rb_codegen_is_large(const rebop_network& net);
 #define RB_VARIANT_EVENTS 2
 std::string rb_codegen_source(const rebop_network& net, const std::string& kernel_name, RbCodegenInfo* info,
                               int variant = RB_VARIANT_GRID);
+
+// Partial-propensity form of a mass-action network (opt-in kernel REBOP_KERNEL_PDM, tier-2 parity); `low` comes from
+// rb_pdm_lower (pdm.hpp).  Entry points <name>, <name>_dyn, <name>_dns.
+struct RbPdmLowered;
+std::string rb_codegen_pdm_source(const rebop_network& net, const RbPdmLowered& low, const std::string& kernel_name,
+                                  RbCodegenInfo* info);

@@ -18,7 +18,7 @@
 #include "network.hpp"
 #include "samples.h"
 #include "ssa_params.h"
-#include "ssa_pdm.h"
+#include "pdm.hpp"
 #include "ssa_table.h"
 
 #define RB_CUDA(call)                                                                          \
@@ -60,8 +60,9 @@ struct rebop_batch {
   bool async_pending = false;    // a launch on a caller-owned stream has not been accounted for yet
   RbTables* d_tables = nullptr;  // table-driven kernel: this batch's network image on the device
   bool tables_uploaded = false;
-  rb_u64* d_pdm = nullptr;       // dependency-driven kernel: this batch's partial-propensity tables on the device
+  rb_u64* d_pdm = nullptr;       // partial-propensity kernel: this batch's tables for the reaction choice on the device
   bool pdm_uploaded = false;
+  RbPdmLowered pdm;              // host lowering (derived constants travel in the launch parameters)
   // a call cut short by the watchdog (REBOP_ERR_ITER_CAP): repeating it with the same arguments continues it
   struct Pending {
     bool active = false;
@@ -619,16 +620,6 @@ static int rb_auto_mode(const rebop_batch* b, double tmax, unsigned n_save, unsi
   return a0 * tmax >= (double)n_save * n_points ? RB_MODE_SPARSE : RB_MODE_DENSE;
 }
 
-// Claiming schedules: the number of last trajectories that are handed out warp-wise (SsaRunParams::endgame), as a
-// share of the resident lanes.  REBOP_B200_ENDGAME=<percent> switches it on (development knob; off by default).
-static unsigned endgame_threshold(unsigned resident_lanes) {
-  static const int percent = [] {
-    const char* env = std::getenv("REBOP_B200_ENDGAME");
-    return env ? std::max(0, std::atoi(env)) : 0;  // measured (gpurun_out/r2d_endgame.log): no gain on any workload, see DESIGN.md
-  }();
-  return (unsigned)((uint64_t)resident_lanes * (unsigned)percent / 100u);
-}
-
 // Pending seeding (rebop_batch_create / rebop_batch_seed) is applied on the stream before the next launch.
 static int apply_seeding(rebop_batch* b) {
   if (b->seed_mode == 0) return REBOP_OK;
@@ -671,18 +662,17 @@ static int upload_tables(rebop_batch* b) {
   return REBOP_OK;
 }
 
-// The dependency-driven kernel reads the batch's partial-propensity tables (ssa_pdm.h); lowered and uploaded once.
+// The partial-propensity kernel: lowering (pdm.hpp) and the device image of its choice tables, once per batch and set of
+// rate constants.
 static int upload_pdm(rebop_batch* b) {
   if (b->pdm_uploaded) return REBOP_OK;
-  std::vector<uint64_t> image;
   std::string why;
-  int st = rb_pdm_build(b->net, &image, &why);
+  int st = rb_pdm_lower(b->net, &b->pdm, &why);
   if (st) return rb_fail(st, why);
   if (b->d_pdm) RB_CUDA(cudaFree(b->d_pdm));
   b->d_pdm = nullptr;
-  RB_CUDA(cudaMalloc(&b->d_pdm, image.size() * sizeof(uint64_t)));
-  RB_CUDA(cudaMemcpyAsync(b->d_pdm, image.data(), image.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
-  RB_CUDA(cudaStreamSynchronize(b->stream));  // `image` goes out of scope
+  RB_CUDA(cudaMalloc(&b->d_pdm, b->pdm.image.size() * sizeof(uint64_t)));
+  RB_CUDA(cudaMemcpyAsync(b->d_pdm, b->pdm.image.data(), b->pdm.image.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
   b->pdm_uploaded = true;
   return REBOP_OK;
 }
@@ -813,9 +803,12 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   int jit_kind = REBOP_KERNEL_NVRTC;
   const bool use_pdm = b->kernel_pref == REBOP_KERNEL_PDM;
   if (use_pdm) {
-    if (!b->x_nonneg) return rb_fail(REBOP_ERR_LIMIT, "the dependency-driven kernel (REBOP_KERNEL_PDM) needs counts >= 0");
+    if (!b->x_nonneg) return rb_fail(REBOP_ERR_LIMIT, "the partial-propensity kernel (REBOP_KERNEL_PDM) needs counts >= 0");
     int st = upload_pdm(b);
+    if (!st) st = rb_jit_get_pdm(b->net, b->pdm, b->device, &jit);
     if (st) return st;
+    use_jit = true;
+    jit_kind = REBOP_KERNEL_PDM;
   } else {
     int st = pick_kernel(b, false, &jit, &use_jit, &jit_kind);
     if (st) return st;
@@ -841,28 +834,10 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
 
   RB_CUDA(cudaEventRecord(b->ev0, b->stream));
   if (use_pdm) {
-    int st = upload_gtab(b, save_idx, p.n_save);  // stoichiometry records + saved-species list
-    if (st) return st;
-    p.gtab = b->d_gtab;
+    for (size_t i = 0; i < b->pdm.consts.size(); ++i) p.k[i] = b->pdm.consts[i];  // c_i, K_ij in the order the kernel reads them
     p.pdm = b->d_pdm;
-    const unsigned block = RB_PDM_BLOCK;
-    const unsigned net_words = rb_pdm_net_words(S);
-    p.ring_depth = claim ? 0u : choose_ring_depth(b, block, net_words, p.n_save, n_points, 2);
-    const size_t smem = RB_SSA_SMEM_BYTES(net_words, block, p.ring_depth, p.n_save);
-    if (smem + RB_STATIC_SMEM_BYTES > (size_t)b->max_smem_optin)
-      return rb_fail(REBOP_ERR_LIMIT, "dependency-driven kernel: per-trajectory state does not fit in shared memory");
-    unsigned grid = (unsigned)((b->n + block - 1) / block);
-    if (claim) {
-      int resident = 0;
-      RB_CUDA(rb_pdm_occupancy(mode, smem, &resident));
-      grid = std::min(grid, (unsigned)std::max(1, resident) * (unsigned)b->sm_count);
-      p.dynamic = 1;
-      p.n_launched = grid * block;
-      p.endgame = endgame_threshold(p.n_launched);
-    }
-    RB_CUDA(rb_pdm_launch(mode, p, grid, smem, b->stream));
-    b->kernel_used = REBOP_KERNEL_PDM;
-  } else if (use_jit) {
+  }
+  if (use_jit) {
     // saved species: the specialised kernels take a bit mask and emit rows in ascending species order
     for (uint32_t j = 0; j < p.n_save && save_idx[j] < 128; ++j) p.save_mask[save_idx[j] >> 6] |= 1ull << (save_idx[j] & 63u);
     const unsigned block = jit.block;
@@ -885,7 +860,6 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
       grid = std::min(grid, (unsigned)std::max(1, resident) * (unsigned)b->sm_count);
       p.dynamic = 1;
       p.n_launched = grid * block;
-      p.endgame = endgame_threshold(p.n_launched);
     }
     int st = rb_jit_launch(jit, mode, p, grid, smem, b->stream);
     if (st) return st;
@@ -912,7 +886,6 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
       grid = std::min(grid, (unsigned)std::max(1, resident) * (unsigned)b->sm_count);
       p.dynamic = 1;
       p.n_launched = grid * block;
-      p.endgame = endgame_threshold(p.n_launched);
     }
     RB_CUDA(rb_table_launch(mode, p, grid, smem, b->stream));
     b->kernel_used = REBOP_KERNEL_TABLE;
@@ -1128,7 +1101,7 @@ struct EventsLaunch {
 static int events_setup(rebop_batch* b, const uint32_t* save_idx, uint32_t n_save, EventsLaunch* e) {
   const uint32_t S = b->net.n_species;
   if (b->kernel_pref == REBOP_KERNEL_PDM)
-    return rb_fail(REBOP_ERR_LIMIT, "the dependency-driven kernel (REBOP_KERNEL_PDM) has no event-log / single-step entry points: "
+    return rb_fail(REBOP_ERR_LIMIT, "the partial-propensity kernel (REBOP_KERNEL_PDM) has no event-log / single-step entry points: "
                                      "use one of the bit-exact kernels");
   int st = pick_kernel(b, true, &e->jit, &e->use_jit, &e->jit_kind);
   if (!st) st = apply_seeding(b);

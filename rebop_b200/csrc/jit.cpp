@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "codegen.hpp"
+#include "pdm.hpp"
 #include "sysgen.hpp"
 
 extern const char* const rb_embedded_names[];
@@ -180,12 +181,23 @@ int rb_jit_compile(const rebop_network& net, std::string* source, std::vector<ch
   return REBOP_OK;
 }
 
+static int jit_get_source(const std::string& src, const RbCodegenInfo& info, int device, RbJitKernel* out);
+
 int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out) {
   std::string why;
   if (!rb_codegen_supported(net, &why)) return rb_fail(REBOP_ERR_LIMIT, "network cannot be specialised: " + why);
   RbCodegenInfo info;
   const std::string src = rb_codegen_source(net, "rb_ssa_jit", &info);
+  return jit_get_source(src, info, device, out);
+}
 
+int rb_jit_get_pdm(const rebop_network& net, const RbPdmLowered& low, int device, RbJitKernel* out) {
+  RbCodegenInfo info;
+  const std::string src = rb_codegen_pdm_source(net, low, "rb_ssa_jit", &info);
+  return jit_get_source(src, info, device, out);
+}
+
+static int jit_get_source(const std::string& src, const RbCodegenInfo& info, int device, RbJitKernel* out) {
   std::lock_guard<std::mutex> lock(g_mutex);
   auto key = std::make_pair(device, src);
   auto it = g_cache.find(key);
@@ -275,6 +287,32 @@ static int copy_out(const char* data, size_t size, char* buf, size_t cap, size_t
   if (needed) *needed = size;
   if (buf && cap) std::memcpy(buf, data, size < cap ? size : cap);
   return REBOP_OK;
+}
+
+// Source / sm_100a cubin of the partial-propensity kernel (REBOP_KERNEL_PDM) of a mass-action network; needs no GPU.
+static int pdm_compile(const rebop_network& net, std::string* source, std::vector<char>* cubin) {
+  RbPdmLowered low;
+  std::string why;
+  int st = rb_pdm_lower(net, &low, &why);
+  if (st) return rb_fail(st, why);
+  const std::string src = rb_codegen_pdm_source(net, low, "rb_ssa_jit", nullptr);
+  if (source) *source = src;
+  if (cubin) return compile_to_cubin(src, cubin);
+  return REBOP_OK;
+}
+extern "C" int rebop_network_codegen_pdm(const rebop_network* net, char* buf, size_t cap, size_t* needed) {
+  if (!net) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  std::string src;
+  int st = pdm_compile(*net, &src, nullptr);
+  if (st) return st;
+  return copy_out(src.c_str(), src.size() + 1, buf, cap, needed);
+}
+extern "C" int rebop_network_jit_cubin_pdm(const rebop_network* net, char* buf, size_t cap, size_t* needed) {
+  if (!net) return rb_fail(REBOP_ERR_INVALID, "NULL argument");
+  std::vector<char> cubin;
+  int st = pdm_compile(*net, nullptr, &cubin);
+  if (st) return st;
+  return copy_out(cubin.data(), cubin.size(), buf, cap, needed);
 }
 
 extern "C" int rebop_network_codegen(const rebop_network* net, char* buf, size_t cap, size_t* needed) {

@@ -23,6 +23,9 @@ struct RbJitKernel {
 // REBOP_ERR_LIMIT when the network is too large to specialise, REBOP_ERR_NVRTC when NVRTC is
 // missing or the compilation fails (the message carries the log).
 int rb_jit_get(const rebop_network& net, int device, RbJitKernel* out);
+// The partial-propensity kernel of a mass-action network (REBOP_KERNEL_PDM; `low` from rb_pdm_lower).
+struct RbPdmLowered;
+int rb_jit_get_pdm(const rebop_network& net, const RbPdmLowered& low, int device, RbJitKernel* out);
 // Same for the event-log kernels (a separate NVRTC program, compiled on first use).
 int rb_jit_get_events(const rebop_network& net, int device, RbJitKernel* out);
 // cudaFuncAttributeMaxDynamicSharedMemorySize of `kernel` on the current device, only ever raised (batches on

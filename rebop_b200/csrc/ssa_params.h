@@ -62,9 +62,6 @@ struct SsaRunParams {
   rb_u32* progress;      // [ldn] see RB_PROGRESS_*
   rb_u32 n_launched;     // dynamic: threads of the grid = trajectories assigned statically at the start
   rb_u32* work_next;     // dynamic: [1] trajectories claimed beyond n_launched (zero before the launch)
-  rb_u32 endgame;        // dynamic: once no more than this many trajectories are unclaimed, a warp claims only as a whole
-                         // (when none of its lanes is running), so that the last trajectories of the ensemble run in
-                         // full warps on a nearly empty machine instead of in a few lanes of every warp (0 = never)
   rb_u32 bias_hi;        // 0x43300000: high word of the biased-double species form (opaque to the compiler on purpose)
   // Constants the hot loop reads straight from the parameter bank (one LDCU.128 per pair) instead of
   // rebuilding them with two UMOVs each per iteration.
@@ -81,7 +78,8 @@ struct SsaRunParams {
                              // (Gillespie::advance_one_reaction, src/gillespie.rs:270-274)
   const rb_u32* gtab;    // table-driven and large specialised kernels: per-reaction records (+ saved-species list)
   const void* tables;    // table-driven kernel: this batch's RbTables image in global memory
-  const void* pdm;       // dependency-driven kernel (ssa_pdm.cu): this batch's partial-propensity tables
+  const rb_u64* pdm;     // partial-propensity kernels: this batch's tables for the reaction choice (pdm.hpp); their
+                         // derived constants c_i, K_ij travel in k[]
   int n_species, n_reactions, arith;  // table-driven kernel: copies of the RbTables scalars
   double k[RB_MAX_K];    // specialised kernels: rate constants (kernel parameters may be up to 32 KB on sm_70+)
 };
