@@ -678,6 +678,97 @@ def run_gpu(args, model):
     return 0
 
 
+def run_single_process(args, model):
+    """`--single-process`: ONE process drives all N GPUs through the C ABI's ensemble handle (rebop_ensemble_*: one
+    batch and one host worker thread per device, contiguous trajectory ranges; the ensemble sums are all-reduced over
+    an ncclCommInitAll communicator inside the library).  Same workload and keys as the torchrun mode; the device time
+    of a step is the slowest device's kernel time (rebop_ensemble_last_kernel_ms)."""
+    from rebop_b200 import _ffi, models
+
+    G = args.gpus
+    if _ffi.device_count() < G:
+        raise SystemExit(f"--single-process --gpus {G}: only {_ffi.device_count()} CUDA device(s) visible")
+    n, nb, S = args.traj_per_gpu * G, args.nb_steps, len(model["species"])
+    arith = _ffi.ARITH_MACRO
+    net = models.build_network(model, arith)
+    ens = _ffi.Ensemble(net, n, model["x0"], list(range(G)), seeds=None, seed_base=0)
+    x0 = np.asarray(model["x0"], dtype=np.int64)
+    samplers = [ClockSampler(g) for g in range(G)]
+    for sm in samplers:
+        sm.start()
+
+    def step(i, host_out=None, host_seeds=None):
+        ens.set_species(x0)
+        ens.set_time(0.0)
+        if host_seeds is None:
+            ens.seed(None, i * n)
+        else:
+            host_seeds[:] = np.arange(i * n, (i + 1) * n, dtype=np.uint64)
+            ens.seed(host_seeds)
+        ens.run_grid(args.tmax, nb, host_out=host_out)
+        return ens.events()[1], ens.last_kernel_ms
+
+    for i in range(args.warmup):
+        step(i)
+    for sm in samplers:
+        sm.mark()
+    launches0 = _ffi.kernel_launches()
+    events = kernel_ms = 0
+    w0 = time.perf_counter()
+    for i in range(args.steps):
+        ev, ms = step(args.warmup + i)
+        events += ev
+        kernel_ms += ms
+    wall = time.perf_counter() - w0
+    launches = _ffi.kernel_launches() - launches0
+    t0 = time.perf_counter()
+    mean, var = ens.stats()          # K4 per device -> ncclAllReduce(int64) -> finalisation kernel
+    stats_ms = (time.perf_counter() - t0) * 1e3
+    clocks = [sm.stop() for sm in samplers]
+
+    e2e = parity = None
+    if not args.no_e2e:
+        host_out = np.empty((nb + 1, S, n), dtype=np.int32)
+        host_seeds = np.empty(n, dtype=np.uint64)
+        for i in range(args.warmup):
+            step(i, host_out, host_seeds)
+        w1 = time.perf_counter()
+        e2e_events = 0
+        for i in range(args.steps):
+            e2e_events += step(args.warmup + i, host_out, host_seeds)[0]
+        e2e_s = time.perf_counter() - w1
+        e2e = {"value": e2e_events / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 8 + S * 8),
+               "d2h_bytes_per_step": int(host_out.nbytes), "ms_per_step": e2e_s / args.steps * 1e3,
+               "host_memory": "pageable", "api": "rebop_ensemble_seed + rebop_ensemble_run_grid(host_out)"}
+        last = args.warmup + args.steps - 1
+        # every device's first trajectories of the last step against the oracle
+        equal, n_chk = True, 0
+        for dev, first, count in ens.shards():
+            k = min(args.parity_n // G or 1, count)
+            chk = oracle_parity(model, arith, np.arange(last * n + first, last * n + first + k, dtype=np.uint64), args.tmax, nb,
+                                host_out[:, :, first:first + k], host_cores())
+            equal, n_chk = equal and chk["equal"], n_chk + k
+        parity = {"n": n_chk, "equal": bool(equal), "what": "first trajectories of every device's shard, last e2e step, vs the oracle"}
+    ens.close()
+    dev_s = kernel_ms * 1e-3
+    line = {
+        "metric": METRIC, "value": events / dev_s, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, G),
+        "mode": "single process, rebop_ensemble_* (one host thread per device; NCCL all-reduce of the ensemble sums in the library)",
+        "wall_ms_per_step": wall / args.steps * 1e3, "value_by_wall_clock": events / wall,
+        "trajectories_per_s": n * args.steps / dev_s, "clocks": clocks[0], "clocks_per_device": clocks, "e2e": e2e,
+        "gpu_launches": launches, "parity_check": parity,
+        "ensemble_stats": {"ms": stats_ms, "collective": "ncclAllReduce(int64 sum) over ncclCommInitAll" if G > 1 else "none (1 GPU)",
+                           "mean_at_tmax": dict(zip(model["species"], mean[-1].tolist()))},
+    }
+    print(json.dumps(line), flush=True)
+    if parity is not None and not parity["equal"]:
+        print("bench.py: PARITY CHECK FAILED: the timed result differs from the oracle", file=sys.stderr)
+        return 3
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -691,6 +782,8 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "table", "nvrtc", "prebuilt"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="one process drives all --gpus devices through the C ABI's ensemble handle (no torchrun)")
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configurations")
     ap.add_argument("--parity-n", type=int, default=256, help="trajectories of the last e2e step recomputed by the oracle")
     ap.add_argument("--config-steps", type=int, default=3)
@@ -712,6 +805,8 @@ def main():
 
     if args.impl == "reference":
         return run_reference(args, model)
+    if args.single_process:
+        return run_single_process(args, model)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
