@@ -104,6 +104,8 @@ struct rebop_ensemble {
   std::vector<size_t> first, count;
   size_t n_total = 0;
   std::vector<ncclComm_t> comms;  // created on the first statistics call over more than one device
+  std::vector<int64_t*> d_reduced;  // per device: the ensemble's sums (the shards' own sums stay what they are, so that
+  size_t reduced_capacity = 0;      // asking twice -- sums, then stats -- reduces the same inputs twice, not the result)
   uint32_t rows = 0;
   uint32_t n_species = 0;
   int sample_bytes = 4;
@@ -136,6 +138,11 @@ extern "C" void rebop_ensemble_destroy(rebop_ensemble* e) {
   if (!e) return;
   for (ncclComm_t c : e->comms)
     if (c) nccl().CommDestroy(c);
+  for (size_t g = 0; g < e->d_reduced.size(); ++g) {
+    if (!e->d_reduced[g]) continue;
+    cudaSetDevice(e->devices[g]);
+    cudaFree(e->d_reduced[g]);
+  }
   for (rebop_batch* b : e->shard) rebop_batch_destroy(b);
   delete e;
 }
@@ -258,7 +265,8 @@ static int first_live(const rebop_ensemble* e) {
   return -1;
 }
 
-// Row sums of every shard, all-reduced in place on the devices (every device ends up with the ensemble's sums).
+// Row sums of every shard, all-reduced on the devices into buffers of the ensemble's own (every device ends up with
+// the ensemble's sums; the shards' sums are left as they are).  *d_sums: where the ensemble's sums are, per device.
 static int reduce_sums(rebop_ensemble* e, std::vector<const int64_t*>* d_sums) {
   const size_t G = e->shard.size();
   d_sums->assign(G, nullptr);
@@ -276,6 +284,23 @@ static int reduce_sums(rebop_ensemble* e, std::vector<const int64_t*>* d_sums) {
     for (size_t h = 0; h < g; ++h) distinct = distinct && !(e->shard[h] && e->devices[h] == e->devices[g]);
   }
   if (live < 2) return REBOP_OK;
+  // receive buffers of the reduction, one per device
+  const size_t need = 2 * (size_t)e->rows;
+  if (e->d_reduced.size() != G || e->reduced_capacity < need) {
+    for (size_t g = 0; g < e->d_reduced.size(); ++g) {
+      if (!e->d_reduced[g]) continue;
+      cudaSetDevice(e->devices[g]);
+      cudaFree(e->d_reduced[g]);
+    }
+    e->d_reduced.assign(G, nullptr);
+    e->reduced_capacity = 0;
+    for (size_t g = 0; g < G; ++g) {
+      if (!e->shard[g]) continue;
+      RB_CUDA(cudaSetDevice(e->devices[g]));
+      RB_CUDA(cudaMalloc(&e->d_reduced[g], need * sizeof(int64_t)));
+    }
+    e->reduced_capacity = need;
+  }
   if (!distinct) {
     // several shards on one device (a way to exercise the sharding on a single GPU): NCCL wants one rank per
     // device, so the few thousand integers are added on the host and handed back to the first shard's buffer
@@ -292,7 +317,8 @@ static int reduce_sums(rebop_ensemble* e, std::vector<const int64_t*>* d_sums) {
     }
     const int g0 = first_live(e);
     RB_CUDA(cudaSetDevice(e->devices[g0]));
-    RB_CUDA(cudaMemcpy(const_cast<int64_t*>((*d_sums)[g0]), total.data(), count * sizeof(int64_t), cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMemcpy(e->d_reduced[g0], total.data(), count * sizeof(int64_t), cudaMemcpyHostToDevice));
+    (*d_sums)[g0] = e->d_reduced[g0];
     return REBOP_OK;
   }
   Nccl& n = nccl();
@@ -314,12 +340,13 @@ static int reduce_sums(rebop_ensemble* e, std::vector<const int64_t*>* d_sums) {
     if (!e->shard[g]) continue;
     void* stream = nullptr;
     rebop_batch_get_stream(e->shard[g], &stream);
-    void* buf = const_cast<int64_t*>((*d_sums)[g]);
-    rc = n.AllReduce(buf, buf, 2 * (size_t)e->rows, kNcclInt64, kNcclSum, e->comms[g], static_cast<cudaStream_t>(stream));
+    rc = n.AllReduce((*d_sums)[g], e->d_reduced[g], 2 * (size_t)e->rows, kNcclInt64, kNcclSum, e->comms[g], static_cast<cudaStream_t>(stream));
   }
   const int rc_end = n.GroupEnd();
   if (rc == 0) rc = rc_end;
   if (rc != 0) return rb_fail(REBOP_ERR_NCCL, std::string("ncclAllReduce: ") + n.GetErrorString(rc));
+  for (size_t g = 0; g < G; ++g)
+    if (e->shard[g]) (*d_sums)[g] = e->d_reduced[g];
   return REBOP_OK;
 }
 
