@@ -13,7 +13,7 @@ mm = rebop_b200.Gillespie()
 mm.add_reaction("V * A / (Km + A)", ["A"], ["P"])
 for rep in range(2):
     t0 = time.perf_counter()
-    ds = mm.run({"A": 100}, tmax=250, nb_steps=100, params={"V": 1, "Km": 20}, rng=0, n_trajectories=n, dtype=np.int32)
+    ds = mm.run({"A": 100}, tmax=250, nb_steps=100, params={"V": 1, "Km": 20}, rng=0, n_trajectories=n, dtype=np.int16)
     dt = time.perf_counter() - t0
     print(f"mm expr n={n}: {dt * 1e3:.1f} ms wall, kernel {mm.last_kernel_ms:.2f} ms, {mm.last_events} events -> "
           f"{n / dt:.4g} traj/s end to end, {mm.last_events / mm.last_kernel_ms * 1e3:.4g} events/s in the kernel; "
