@@ -996,7 +996,11 @@ static int copy_rows_to_host(rebop_batch* b, void* host, size_t host_ld, size_t 
     if (!b->ev_stage[i]) RB_CUDA(cudaEventCreateWithFlags(&b->ev_stage[i], cudaEventDisableTiming));
   }
   const size_t chunk_rows = std::max<size_t>(1, RB_STAGE_BYTES / row_bytes);
-  const unsigned n_threads = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2u));
+  static const unsigned n_threads = [] {
+    unsigned t = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char* env = std::getenv("REBOP_B200_COPY_THREADS")) t = (unsigned)std::max(1, std::atoi(env));
+    return t;
+  }();
   auto drain = [&](int slot, size_t r0, size_t nr) -> int {  // staging slot -> caller's rows [r0, r0 + nr)
     RB_CUDA(cudaEventSynchronize(b->ev_stage[slot]));
     char* dst = static_cast<char*>(host) + r0 * host_ld * sb;
