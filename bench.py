@@ -273,7 +273,8 @@ class _HostBuffer:
             self._pin.close()
 
 
-def bench_config(tag, model, arith, n, sample_dtype, ctx, steps, warmup, save_idx=None, parity_n=64, scaling="weak"):
+def bench_config(tag, model, arith, n, sample_dtype, ctx, steps, warmup, save_idx=None, parity_n=64, scaling="weak",
+                 fast_kernel=False):
     """One BASELINE configuration as a short run on this rank's GPU: device-resident and end-to-end through the C ABI
     (host buffers in the timed region), FP64-issue roofline fraction, lane efficiency and an oracle check of the first
     trajectories of the last end-to-end step.  ctx: rank/world/local, reducers, ffi/models modules, fp64 peak."""
@@ -341,6 +342,32 @@ def bench_config(tag, model, arith, n, sample_dtype, ctx, steps, warmup, save_id
                            host_out.array[:, :, :n_chk], host_cores(), save_idx)
     parity["equal"] = bool(ctx["min"](1.0 if parity["equal"] else 0.0) == 1.0)
     host_mem = host_out.kind
+    # ---- optional: the opt-in partial-propensity kernel on the same workload (tier-2 parity: it is the direct method
+    # with differently ordered floating-point sums, so it is checked here through the ensemble mean of the last sample
+    # row against the bit-exact run above -- different seeds would do as well -- and through tests/test_pdm.py)
+    fast = None
+    if fast_kernel:
+        exact_last = host_out.array[-1].astype(np.float64)        # last e2e step of the bit-exact kernel, seeds base(last)
+        fb = _ffi.Batch(net, n, model["x0"], seeds=None, seed_base=base(0), device=local, kernel=_ffi.KERNEL_PDM)
+        fb.set_sample_dtype(dtype)
+        fev = fms = 0
+        for i in range(warmup + steps):
+            fb.set_species(x0)
+            fb.set_time(0.0)
+            fb.seed(None, base(10**6 + i))                        # seeds the bit-exact runs did not use
+            fb.run_grid(tmax, nb, save_idx=save_idx)
+            if i >= warmup:
+                fev += fb.events()[1]
+                fms += fb.last_kernel_ms + fb.last_finish_ms
+        fast_last = fb.samples()[-1].astype(np.float64)
+        fb.close()
+        se = np.sqrt(exact_last.var(axis=1, ddof=1) / n + fast_last.var(axis=1, ddof=1) / n)
+        zmax = float(np.max(np.abs(exact_last.mean(axis=1) - fast_last.mean(axis=1)) / np.maximum(se, 1e-300)))
+        fast = {"kernel": "REBOP_KERNEL_PDM (partial propensities; statistically exact, opt-in)",
+                "value": ctx["sum"](float(fev)) / (ctx["max"](fms) * 1e-3), "unit": UNIT, "ms_per_step": fms / steps,
+                "speedup_vs_bit_exact": None,
+                "check": {"what": "ensemble means of the last sample row vs the bit-exact kernel (independent seeds), in standard errors",
+                          "max_z": zmax, "ok": bool(ctx["min"](1.0 if zmax < 5.0 else 0.0) == 1.0)}}
     host_out.close()
     host_seeds.close()
     b.close()
@@ -359,6 +386,7 @@ def bench_config(tag, model, arith, n, sample_dtype, ctx, steps, warmup, save_id
         "frac": achieved / ctx["fp64_peak"], "ops_per_event": F, "lane_efficiency": events / slots if slots else None,
         "events_per_trajectory": events / (n * steps), "kernel": kernel_used, "schedule": schedule_used, "steps": steps,
         "warmup": warmup, "parity_check": parity,
+        **({"fast_kernel": dict(fast, speedup_vs_bit_exact=fast["value"] / (tot_events / (dev_ms * 1e-3)))} if fast else {}),
     }
 
 
@@ -651,10 +679,11 @@ def run_gpu(args, model):
             # C5: synthetic 100 x 500 network, function-API arithmetic, 10^6 trajectories sharded over the GPUs (strong
             # scaling); the first 10 species are returned (all 100 would be 40 GB of int32 per step)
             "C5_synthetic_api": bench_config("C5", models.synthetic(), _ffi.ARITH_API, max(1, n1 // world), np.int32, ctx, cs, cw,
-                                             save_idx=list(range(10)), parity_n=16, scaling="strong"),
+                                             save_idx=list(range(10)), parity_n=16, scaling="strong", fast_kernel=True),
         }
     all_equal = all(v is True for v in [parity and parity["equal"]] +
-                    [c["parity_check"]["equal"] for c in (configs or {}).values()] if v is not None)
+                    [c["parity_check"]["equal"] for c in (configs or {}).values()] +
+                    [c["fast_kernel"]["check"]["ok"] for c in (configs or {}).values() if "fast_kernel" in c] if v is not None)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

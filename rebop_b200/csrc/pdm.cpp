@@ -1,6 +1,7 @@
 // pdm.cpp -- lowering of a mass-action network into its partial-propensity form (pdm.hpp).
 #include "pdm.hpp"
 
+#include <algorithm>
 #include <cstring>
 
 #include "ssa_params.h"
@@ -88,15 +89,26 @@ int rb_pdm_lower(const rebop_network& net, RbPdmLowered* out, std::string* why) 
   out->image.assign(off + 2, 0);
   uint32_t* bp = reinterpret_cast<uint32_t*>(out->image.data() + header[1]);
   uint64_t* ew = out->image.data() + header[2];
+  // Inside a block the walk defines the sub-intervals itself (the unrolled pass only fixes the block sums), so the
+  // reactions of a block may come in any order: the ones likely to carry most of the block's propensity first, so
+  // that most lanes leave the walk after its first step.  The weight is a static guess -- rate constant, times a
+  // typical count for the partner of a second-order reaction -- and only affects speed.
+  struct Entry { double k; uint32_t i, j, reaction, kind; double weight; };
   uint32_t ne = 0;
-  for (unsigned g = 0; g < ng; ++g) {
-    if (g % out->group_size == 0) bp[g / out->group_size] = ne;
-    const RbPdmGroup& grp = out->groups[g];
-    for (const RbPdmGroup::Own& e : grp.own) {
-      const uint32_t kind = e.partner == RB_PDM_NONE ? 0u : e.partner == grp.species ? 2u : 1u;
-      const uint32_t j = kind == 1u ? e.partner : grp.species;
+  for (unsigned b0 = 0; b0 < ng; b0 += out->group_size) {
+    bp[b0 / out->group_size] = ne;
+    std::vector<Entry> block;
+    for (unsigned g = b0; g < ng && g < b0 + out->group_size; ++g) {
+      const RbPdmGroup& grp = out->groups[g];
+      for (const RbPdmGroup::Own& e : grp.own) {
+        const uint32_t kind = e.partner == RB_PDM_NONE ? 0u : e.partner == grp.species ? 2u : 1u;
+        block.push_back({e.k, grp.species, kind == 1u ? e.partner : grp.species, e.reaction, kind, e.k * (kind ? 100.0 : 1.0)});
+      }
+    }
+    std::stable_sort(block.begin(), block.end(), [](const Entry& a, const Entry& b) { return a.weight > b.weight; });
+    for (const Entry& e : block) {
       std::memcpy(ew + 2 * ne, &e.k, 8);
-      ew[2 * ne + 1] = (uint64_t)(grp.species | (j << 16)) | ((uint64_t)(e.reaction | (kind << 30)) << 32);
+      ew[2 * ne + 1] = (uint64_t)(e.i | (e.j << 16)) | ((uint64_t)(e.reaction | (e.kind << 30)) << 32);
       ++ne;
     }
   }

@@ -33,7 +33,7 @@ struct RbPdmLowered {
   //   header {u32 n_blocks, off_block_ptr, off_entries, n_entries}
   //   block_ptr[n_blocks + 1]  u32: the reactions owned by the groups of checkpoint block b are entries [ptr[b], ptr[b+1])
   //   entries[]                {f64 k; u32 i | j << 16; u32 reaction | kind << 30}  (16 bytes), kind 0: a = k x_i,
-  //                            1: a = k x_i x_j, 2: a = k x_i (x_i - 1); in the order of the unrolled pass
+  //                            1: a = k x_i x_j, 2: a = k x_i (x_i - 1); blocks in the order of the unrolled pass, inside a block heaviest first
   std::vector<uint64_t> image;
 };
 

@@ -117,3 +117,24 @@ def test_pdm_is_opt_in_and_refuses_event_logs(gpu, ffi):
     with pytest.raises(ffi.RebopError, match="event-log"):
         b.run_events(1.0)
     b.close()
+
+
+@pytest.mark.gpu
+def test_python_front_end_fast_kernel(gpu, oracle):
+    """`Gillespie.run(..., kernel="fast")`: the binding's switch for the partial-propensity kernel; same law as the
+    default kernel (tier 2), and refused with the reason for a network the form cannot express."""
+    import rebop_b200
+
+    sir = rebop_b200.Gillespie()
+    sir.add_reaction(1e-4, ["S", "I"], ["I", "I"])
+    sir.add_reaction(0.01, ["I"], ["R"])
+    n = 20000
+    fast = sir.run({"S": 999, "I": 1}, tmax=250, nb_steps=10, rng=1, n_trajectories=n, kernel="fast", dtype=np.int32)
+    exact = sir.run({"S": 999, "I": 1}, tmax=250, nb_steps=10, rng=2, n_trajectories=n, dtype=np.int32)
+    a = np.stack([np.asarray(fast[v]) for v in ("S", "I", "R")], axis=1)
+    b = np.stack([np.asarray(exact[v]) for v in ("S", "I", "R")], axis=1)
+    assert compare_ensembles(a, b, ALPHA, Z) == []
+    mm = rebop_b200.Gillespie()
+    mm.add_reaction("V * A / (Km + A)", ["A"], ["P"])
+    with pytest.raises(Exception, match="expression rate"):
+        mm.run({"A": 100}, tmax=1, nb_steps=1, params={"V": 1, "Km": 20}, n_trajectories=8, kernel="fast")
