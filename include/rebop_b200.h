@@ -52,16 +52,18 @@ typedef enum {
 /* Which kernel advances the ensemble. */
 typedef enum {
   REBOP_KERNEL_AUTO = 0,   /* build-time kernel if one matches, else NVRTC-specialised, else table-driven */
-  REBOP_KERNEL_TABLE = 1,  /* K1: generic kernel, network tables in __constant__ memory */
+  REBOP_KERNEL_TABLE = 1,  /* K1: generic kernel, network tables in global memory (one image per batch) */
   REBOP_KERNEL_NVRTC = 2,  /* K2: network-specialised source compiled at run time */
   REBOP_KERNEL_PREBUILT = 3, /* K2: network-specialised source compiled at build time (rebop_sysgen + nvcc) */
-  REBOP_KERNEL_PDM = 4     /* K6: dependency-driven kernel for large mass-action networks (partial propensities, sums
-                            * updated incrementally).  OPT-IN and never picked by AUTO: it is the direct method with the
-                            * reference's random-number consumption, but its floating-point sums round differently from the
-                            * reference's running sum, so results are statistically exact, not bit-identical.  Fills the
+  REBOP_KERNEL_PDM = 4     /* K7: partial-propensity kernel for large mass-action networks: the sum of the propensities
+                            * factored by owner species (one fused multiply-add per species and reactant pair instead of
+                            * two to three multiplies and an add per reaction).  OPT-IN and never picked by AUTO: it is the
+                            * direct method with the reference's random-number consumption, but its floating-point sums are
+                            * ordered and fused differently from the reference's running sum, so results are statistically
+                            * exact, not bit-identical (parity by ensemble statistics, tests/test_pdm.py).  Fills the
                             * "heuristics for large systems" the reference's binding promises and does not have
                             * (python/rebop/gillespie.py:123-126, src/pyo3_gillespie.rs:161).  Needs elementary mass
-                            * action (total order <= 2), k >= 0, counts that cannot go negative. */
+                            * action (total order <= 2), k >= 0, counts that cannot go negative; no event-log mode. */
 } rebop_kernel_kind;
 
 /* Sample type of a batch's time-grid results (the value is the size in bytes).  The reference returns isize

@@ -38,7 +38,7 @@ __device__ __forceinline__ void bulk_store(void* dst, const void* src_shared, un
 }
 
 template <typename OutT, bool BULK>
-__global__ void __launch_bounds__(kThreads) rb_samples_finish_kernel(const RbFinishParams q) {
+__global__ void __launch_bounds__(kThreads, 2048 / kThreads) rb_samples_finish_kernel(const RbFinishParams q) {
   __shared__ __align__(128) Tile<OutT> tile;
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const unsigned row0 = blockIdx.x * kRows;
@@ -142,9 +142,15 @@ template <typename OutT>
 cudaError_t finish_typed(const RbFinishParams& q, bool bulk, unsigned sm_count, cudaStream_t stream) {
   const unsigned row_blocks = (q.rows + kRows - 1) / kRows;
   const unsigned n_tiles = (q.ldn + kTraj - 1) / kTraj;
-  // enough CTAs to fill the machine a few times over; every CTA walks a strided share of the trajectory tiles, so
-  // that the row sums cost one atomic per (row, CTA column) instead of one per tile
-  unsigned cols = (sm_count * 8u + row_blocks - 1) / row_blocks;
+  // One wave of resident CTAs (the kernel waits on its reads: a partial second wave runs at a fraction of the
+  // bandwidth -- ncu, profiles/r2r_k6_finish_int16_ncu_full.md: 1200 CTAs on 888 slots, 1.35 waves); every CTA walks a
+  // strided share of the trajectory tiles, so that the row sums cost one atomic per (row, CTA column) instead of one
+  // per tile
+  int resident = 0;
+  if (bulk) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, rb_samples_finish_kernel<OutT, true>, kThreads, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, rb_samples_finish_kernel<OutT, false>, kThreads, 0);
+  if (resident < 1) resident = 1;
+  unsigned cols = std::max(1u, sm_count * (unsigned)resident / row_blocks);
   if (cols > n_tiles) cols = n_tiles;
   if (cols > 65535u) cols = 65535u;
   if (cols == 0) cols = 1;
