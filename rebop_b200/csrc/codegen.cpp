@@ -302,7 +302,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   // Resident CTAs asked of the compiler: as many (up to 5 = 96 registers per thread, the Vilar sweet spot)
   // as leave room for the register-resident state (2 per species), cumulative rates (2 per reaction) and
   // ~40 registers of loop state; larger networks get fewer CTAs instead of spills.
-  unsigned block = 128, minctas = 5, tick = 16, unroll = 1, conv = 0;
+  unsigned block = 128, minctas = 5, tick = 16, unroll = 1, conv = 0, prescale = 1;
   {
     const unsigned need = 2u * (unsigned)S + 2u * (unsigned)R + RB_GEN_LOOP_REGISTERS_TIGHT((unsigned)S, (unsigned)R);
     while (minctas > 1 && std::min(255u, 65536u / (128u * minctas) / 8u * 8u) < need) --minctas;
@@ -318,6 +318,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
     tick = get("tick", tick);
     unroll = get("unroll", unroll);
     conv = get("conv", conv);
+    prescale = get("prescale", prescale);
   }
   if (info) {
     info->block = block;
@@ -453,21 +454,25 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
     o << "    return 0;\n  }\n";
     o << "  __device__ __forceinline__ void apply(const SsaRunParams&, int, rb_u32&) {\n";
   } else {
+    // The value handed from select()/none() to apply() is the byte offset of the reaction's stoichiometry row, not
+    // its index: that saves the shift in front of the row's load (+0.4 %, profiles/r2t_sweep.log; knob prescale=0)
+    const int rs = prescale ? 4 * dwp : 1;
     if (!macro) {
       // choose_cumrate_sum (src/gillespie.rs:402-407): index = number of cum < chosen (two
       // interleaved counters halve the dependency chain)
       o << "    int i = 0, i2 = 0;\n";
-      for (int r = 0; r < R; ++r) o << "    rb_count_lt(" << ((r & 1) ? "i2" : "i") << ", c[" << r << "], chosen);\n";
+      for (int r = 0; r < R; ++r)
+        o << "    rb_count_lt_by<" << rs << ">(" << ((r & 1) ? "i2" : "i") << ", c[" << r << "], chosen);\n";
       o << "    i += i2;\n";
-      o << "    i = i < " << R - 1 << " ? i : " << R - 1 << ";\n";
+      o << "    i = i < " << (R - 1) * rs << " ? i : " << (R - 1) * rs << ";\n";
     } else {
       // _choice! (src/gillespie_macro.rs:150-171): first r with chosen < c[r]; none => nothing happens.
       // Two half-range chains, joined by a min, halve the dependency chain.
       const int H = R / 2;
-      o << "    int i = " << R << ", i2 = " << R << ";\n";
+      o << "    int i = " << R * rs << ", i2 = " << R * rs << ";\n";
       for (int r = R - 1; r >= H; --r) {
-        o << "    rb_first_lt<" << r << ">(i2, chosen, c[" << r << "]);\n";
-        if (r - H >= 0 && r - H < H) o << "    rb_first_lt<" << r - H << ">(i, chosen, c[" << r - H << "]);\n";
+        o << "    rb_first_lt<" << r * rs << ">(i2, chosen, c[" << r << "]);\n";
+        if (r - H >= 0 && r - H < H) o << "    rb_first_lt<" << (r - H) * rs << ">(i, chosen, c[" << r - H << "]);\n";
       }
       if (R % 2) o << "    rb_first_lt<0>(i, chosen, c[0]);\n";
       o << "    i = min(i, i2);\n";
@@ -477,14 +482,15 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
     // matched, src/gillespie_macro.rs:150-171; any arithmetic: the ensemble loop's lanes without an event)
     o << "  __device__ __forceinline__ void apply(const SsaRunParams& p, int i, rb_u32& nev) {\n";
     // fetch the packed stoichiometry row of reaction i from shared memory
+    const std::string row = prescale ? "(rb_u32)i" : std::to_string(4 * dwp) + "u * i";
     if (dwp == 1) {
-      o << "    const int w0 = rb_lds_i32(tab + 4u * i);\n";
+      o << "    const int w0 = rb_lds_i32(tab + " << row << ");\n";
     } else if (dwp == 2) {
-      o << "    const int2 v0 = rb_lds_i32x2(tab + 8u * i);\n";
+      o << "    const int2 v0 = rb_lds_i32x2(tab + " << row << ");\n";
       o << "    const int w0 = v0.x, w1 = v0.y;\n";
     } else {
       for (int q = 0; q < dwp / 4; ++q) {
-        o << "    const int4 v" << q << " = rb_lds_i32x4(tab + " << 4 * dwp << "u * i + " << 16 * q << "u);\n";
+        o << "    const int4 v" << q << " = rb_lds_i32x4(tab + " << row << " + " << 16 * q << "u);\n";
         o << "    const int w" << 4 * q << " = v" << q << ".x, w" << 4 * q + 1 << " = v" << q << ".y, w" << 4 * q + 2
           << " = v" << q << ".z, w" << 4 * q + 3 << " = v" << q << ".w;\n";
       }
@@ -506,7 +512,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   }
   o << "  }\n";
 
-  o << "  static __device__ __forceinline__ int none() { return " << R << "; }\n";
+  o << "  static __device__ __forceinline__ int none() { return " << R * (prescale ? 4 * dwp : 1) << "; }\n";
   // samples: saved species in ascending index order, selected by a launch-time bit mask
   o << "  __device__ __forceinline__ void record(const SsaRunParams& p, int* dst, rb_u32 stride) const {\n";
   o << "    rb_u32 row = 0;\n";
