@@ -298,11 +298,13 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
     for (int s = 0; s < S; ++s)
       if (rx.diff[s] != 0) touched[s] = true;
 
-  // development knobs (REBOP_B200_CODEGEN="block=128,minctas=0,tick=16"); the defaults are the tuned values
+  // development knobs (REBOP_B200_CODEGEN="block=128,minctas=0,tick=32"); the defaults are the tuned values
+  // (tick 32: a lane whose trajectory ends leaves the pass loop until the next tick, so a longer tick costs idle lane
+  // slots and saves tick code; +1 % on Vilar, Dimers and Michaelis-Menten, profiles/r2v_sweep.log)
   // Resident CTAs asked of the compiler: as many (up to 5 = 96 registers per thread, the Vilar sweet spot)
   // as leave room for the register-resident state (2 per species), cumulative rates (2 per reaction) and
   // ~40 registers of loop state; larger networks get fewer CTAs instead of spills.
-  unsigned block = 128, minctas = 5, tick = 16, unroll = 1, conv = 0, prescale = 1;
+  unsigned block = 128, minctas = 5, tick = 32, unroll = 1, conv = 0, prescale = 1;
   {
     const unsigned need = 2u * (unsigned)S + 2u * (unsigned)R + RB_GEN_LOOP_REGISTERS_TIGHT((unsigned)S, (unsigned)R);
     while (minctas > 1 && std::min(255u, 65536u / (128u * minctas) / 8u * 8u) < need) --minctas;

@@ -652,6 +652,7 @@ static void fill_params(const rebop_batch* b, SsaRunParams* p) {
   p->ldn = (rb_u32)b->ldn;
   p->max_iters = b->max_iters;
   p->bias_hi = 0x43300000u;
+  p->exp_one = 0x3ffu;
   p->bias = 0x1.0p52 + 0x1.0p31;
   p->one_m_eps = 1.0 - 0x1.0p-53;
   for (int l = 0; l < 4; ++l) p->byte_sel[l] = 1 << (8 * l);

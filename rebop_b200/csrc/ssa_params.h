@@ -63,6 +63,7 @@ struct SsaRunParams {
   rb_u32 n_launched;     // dynamic: threads of the grid = trajectories assigned statically at the start
   rb_u32* work_next;     // dynamic: [1] trajectories claimed beyond n_launched (zero before the launch)
   rb_u32 bias_hi;        // 0x43300000: high word of the biased-double species form (opaque to the compiler on purpose)
+  rb_u32 exp_one;        // 0x3ff: exponent field of 1.0, funnel-shifted into the ziggurat's mantissa word (opaque likewise)
   // Constants the hot loop reads straight from the parameter bank (one LDCU.128 per pair) instead of
   // rebuilding them with two UMOVs each per iteration.
   double bias;           // 2^52 + 2^31
