@@ -355,12 +355,13 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   }
   o << "#include \"ssa_kernel.cuh\"\n\n";
 
-  // packed stoichiometry table
-  o << "__constant__ int rb_delta_c[" << (R + 1) * dwp << "] = {";
-  for (int r = 0; r < R; ++r) {
+  // packed stoichiometry table.  Function-API arithmetic: rows 0..R-1, then the all-zero "no reaction" row.
+  // define_system! arithmetic: the all-zero row FIRST, then the reactions in descending order (row R - r): the
+  // first-match chains of select() then start from the zero register and join by a max, one instruction less per pass.
+  auto emit_row = [&](int r, bool first) {
     for (int w = 0; w < dwp; ++w) {
       unsigned word = 0;
-      for (int l = 0; l < per_word; ++l) {
+      for (int l = 0; l < per_word && r >= 0; ++l) {
         const int s = w * per_word + l;
         if (s > S) continue;
         const long long d = s == S ? 1 : net.rx[r].diff[s];
@@ -368,11 +369,18 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
         else word |= ((unsigned)(d & 0xff)) << (8 * l);
       }
       char buf[32];
-      std::snprintf(buf, sizeof buf, "%s0x%08x", (r || w) ? ", " : "", word);
+      std::snprintf(buf, sizeof buf, "%s0x%08x", (first && w == 0) ? "" : ", ", word);
       o << buf;
     }
+  };
+  o << "__constant__ int rb_delta_c[" << (R + 1) * dwp << "] = {";
+  if (macro) {
+    emit_row(-1, true);
+    for (int r = R - 1; r >= 0; --r) emit_row(r, false);
+  } else {
+    for (int r = 0; r < R; ++r) emit_row(r, r == 0);
+    emit_row(-1, R == 0);
   }
-  for (int w = 0; w < dwp; ++w) o << (R || w ? ", " : "") << "0x00000000";
   o << "};\n\n";
 
   o << "struct RbGenNet {\n";
@@ -469,15 +477,15 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
       o << "    i = i < " << (R - 1) * rs << " ? i : " << (R - 1) * rs << ";\n";
     } else {
       // _choice! (src/gillespie_macro.rs:150-171): first r with chosen < c[r]; none => nothing happens.
-      // Two half-range chains, joined by a min, halve the dependency chain.
+      // Two half-range chains walked from the last reaction down, joined by a max (rows are stored in descending
+      // order behind the all-zero row, see above), halve the dependency chain.
       const int H = R / 2;
-      o << "    int i = " << R * rs << ", i2 = " << R * rs << ";\n";
+      o << "    int i = 0, i2 = 0;\n";
       for (int r = R - 1; r >= H; --r) {
-        o << "    rb_first_lt<" << r * rs << ">(i2, chosen, c[" << r << "]);\n";
-        if (r - H >= 0 && r - H < H) o << "    rb_first_lt<" << (r - H) * rs << ">(i, chosen, c[" << r - H << "]);\n";
+        o << "    rb_first_lt<" << (R - r) * rs << ">(i2, chosen, c[" << r << "]);\n";
+        if (r - H >= 0 && r - H < H) o << "    rb_first_lt<" << (R - (r - H)) * rs << ">(i, chosen, c[" << r - H << "]);\n";
       }
-      if (R % 2) o << "    rb_first_lt<0>(i, chosen, c[0]);\n";
-      o << "    i = min(i, i2);\n";
+      o << "    i = max(i, i2);\n";
     }
     o << "    return i;\n  }\n";
     // row R of the table is all zeros: applying it is the branch-free \"no reaction\" (macro arithmetic: nothing
@@ -514,7 +522,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   }
   o << "  }\n";
 
-  o << "  static __device__ __forceinline__ int none() { return " << R * (prescale ? 4 * dwp : 1) << "; }\n";
+  o << "  static __device__ __forceinline__ int none() { return " << (macro ? 0 : R * (prescale ? 4 * dwp : 1)) << "; }\n";
   // samples: saved species in ascending index order, selected by a launch-time bit mask
   o << "  __device__ __forceinline__ void record(const SsaRunParams& p, int* dst, rb_u32 stride) const {\n";
   o << "    rb_u32 row = 0;\n";
