@@ -325,7 +325,8 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   if (info) {
     info->block = block;
     info->net_words = 0;  // the stoichiometry table is static shared memory of the generated kernel
-    info->static_smem = (unsigned)(4 * (R + 1) * dwp);
+    // + the second half of the wide ziggurat tables (RB_ZIG_WIDE, ssa_kernel.cuh) beyond RB_STATIC_SMEM_BYTES
+    info->static_smem = (unsigned)(4 * (R + 1) * dwp) + RB_ZIG_WIDE_EXTRA_BYTES;
     info->uses_param_k = true;
   }
 
@@ -334,6 +335,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
     << (macro ? "define_system! arithmetic" : "function-API arithmetic") << "\n";
   o << "#define RB_NET_STATIC_WORDS " << ((R + 1) * dwp) << "\n";  // + one all-zero row: \"no reaction\"
   o << "#define RB_TICK " << tick << "u\n";
+  o << "#define RB_ZIG_WIDE\n";
   if (unroll != 1) o << "#define RB_INNER_UNROLL " << unroll << "\n";
   if (conv == 1) o << "#define RB_STATE_INT\n";
   if (const char* env = std::getenv("REBOP_B200_CODEGEN")) {  // defs=RB_A+RB_B: experimental switches of ssa_kernel.cuh

@@ -10,6 +10,8 @@ typedef unsigned int rb_u32;
 // Static shared memory of the ensemble loop (ziggurat tables: 256 (X[i], X[i+1]) pairs, 256 (F[i], F[i+1]) pairs,
 // 256 chord slopes)
 #define RB_STATIC_SMEM_BYTES ((512 + 512 + 256) * 8)
+// RB_ZIG_WIDE kernels (the register-resident specialised form) hold five 16-byte entries per layer instead
+#define RB_ZIG_WIDE_EXTRA_BYTES (256 * 16 * 5 - RB_STATIC_SMEM_BYTES)
 
 // Rate constants carried in the launch parameters (bounds the reactions a specialised kernel can have).
 #define RB_MAX_K 1024
