@@ -332,6 +332,35 @@ def test_both_variants_bit_exact_vs_oracle(gpu, ffi, oracle, kernel, arith, name
     b.close()
 
 
+@pytest.mark.parametrize("kernel", ["table", "nvrtc", "prebuilt"])
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("schedule", [1, 2, 3])
+@pytest.mark.parametrize("log2_scale", [-600, -498, 499, 600])
+@pytest.mark.parametrize("name,n,tmax,nb_steps", [("sir", 600, 250.0, 25), ("dimers", 200, 0.5, 3)])
+def test_totals_outside_the_short_divide_range(gpu, ffi, oracle, kernel, arith, schedule, log2_scale, name, n, tmax,
+                                               nb_steps):
+    """The pass divides with a short sequence that is exact for totals in [2^-500, 2^500) and sends every other
+    total through its side exit (IEEE divide).  Rate constants scaled by 2^s and the horizon by 2^-s put the
+    totals below, across and above that range; the oracle divides in IEEE arithmetic throughout."""
+    model = models.MODELS[name]()
+    scale = 2.0 ** log2_scale
+    model["reactions"] = [(k * scale, terms, diff) for k, terms, diff in model["reactions"]]
+    model["params"] = [k * scale for k in model["params"]]
+    tmax = tmax / scale
+    net = models.build_network(model, arith)
+    if kernel == "prebuilt" and not net.has_prebuilt:
+        pytest.skip("no build-time kernel for this network")
+    seeds = numpy_seeds(n, rng=13)
+    ref, _, ref_tot = oracle_network(oracle, model, arith).run_batch(model["x0"], seeds, tmax, nb_steps, threads=8)
+    assert ref_tot > 10 * n
+    b = ffi.Batch(net, n, model["x0"], seeds=seeds, kernel={"table": 1, "nvrtc": 2, "prebuilt": 3}[kernel])
+    b.set_schedule(schedule)
+    b.run_grid(tmax, nb_steps)
+    np.testing.assert_array_equal(b.samples(), ref)
+    assert b.events()[0] == ref_tot
+    b.close()
+
+
 @pytest.mark.parametrize("kernel", ["table", "nvrtc"])
 def test_dynamic_schedule_is_bit_exact(gpu, ffi, oracle, kernel):
     """More trajectories than resident lanes: lanes claim further trajectories from the work counter; the
