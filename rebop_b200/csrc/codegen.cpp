@@ -162,6 +162,7 @@ static std::string large_source(const rebop_network& net, const std::string& ker
   o << "#include \"ssa_kernel.cuh\"\n\n";
   o << "struct RbGenNet {\n";
   o << "  static constexpr int BLOCK = " << block << ";\n";
+  o << "  static constexpr bool NAN_PICKS_NONE = false;\n";
   o << "  double* xs;  // this thread's column of the f64 state: species s at xs[s * BLOCK]\n";
   o << "  double ck[" << nck << "];  // cumulative rate after every " << ckn << " reactions\n";
   o << "  static __device__ __forceinline__ int smem_words(const SsaRunParams&) { return " << S * (int)block * 2 << "; }\n";
@@ -240,6 +241,7 @@ std::string rb_codegen_pdm_source(const rebop_network& net, const RbPdmLowered& 
   o << "#include \"ssa_kernel.cuh\"\n\n";
   o << "struct RbGenNet {\n";
   o << "  static constexpr int BLOCK = " << block << ";\n";
+  o << "  static constexpr bool NAN_PICKS_NONE = false;\n";
   o << "  double* xs;  // this thread's column of the f64 state: species s at xs[s * BLOCK]; xs[" << S << " * BLOCK] is the constant 1\n";
   o << "  double ck[" << nck << "];  // running sum of x_i * pi_i after every " << gs << " owner groups\n";
   o << "  static __device__ __forceinline__ int smem_words(const SsaRunParams&) { return " << (S + 1) * (int)block * 2 << "; }\n";
@@ -387,6 +389,9 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
 
   o << "struct RbGenNet {\n";
   o << "  static constexpr int BLOCK = " << block << ";\n";
+  // define_system! arithmetic: a NaN `chosen` matches no reaction (first-match chains), see rb_ssa_loop
+  o << "#ifdef RB_X_NO_NANPICK\n  static constexpr bool NAN_PICKS_NONE = false;\n#else\n";
+  o << "  static constexpr bool NAN_PICKS_NONE = " << (macro ? "true" : "false") << ";\n#endif\n";
   o << "  rb_state x[" << (S ? S : 1) << "];  // biased-double form, see ssa_kernel.cuh\n";
   o << "  double c[" << (R ? R : 1) << "];\n";
   o << "  static __device__ __forceinline__ int smem_words(const SsaRunParams&) { return 0; }\n";

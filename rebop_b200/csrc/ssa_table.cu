@@ -22,6 +22,7 @@
 
 struct RbTableNet {
   static constexpr int BLOCK = RB_TABLE_BLOCK;
+  static constexpr bool NAN_PICKS_NONE = false;
   int* xs;  // this thread's column: species s at xs[s * BLOCK]
   const RbTables* __restrict__ tab;
   int n_reactions, arith;
