@@ -173,6 +173,7 @@ static std::string large_source(const rebop_network& net, const std::string& ker
   o << "  __device__ __forceinline__ void store(const SsaRunParams& p, rb_u32 traj) {\n";
   o << "    for (int s = 0; s < " << S << "; ++s) p.x[(size_t)s * p.ldn + traj] = __double2int_rn(xs[s * BLOCK]);\n  }\n";
   // unrolled propensities; the arithmetic of every term is the one rb_large_term re-walks
+  o << "  double tot;\n  __device__ __forceinline__ double& total_ref(const SsaRunParams& p) {\n    tot = propensities(p);\n    return tot;\n  }\n";
   o << "  __device__ __forceinline__ double propensities(const SsaRunParams& p) {\n";
   o << "    double c = 0.0, a;\n";
   if (R == 0) o << "    (void)a;\n";
@@ -252,6 +253,7 @@ std::string rb_codegen_pdm_source(const rebop_network& net, const RbPdmLowered& 
   o << "    xs[" << S << " * BLOCK] = valid ? 1.0 : 0.0;\n  }\n";
   o << "  __device__ __forceinline__ void store(const SsaRunParams& p, rb_u32 traj) {\n";
   o << "    for (int s = 0; s < " << S << "; ++s) p.x[(size_t)s * p.ldn + traj] = __double2int_rn(xs[s * BLOCK]);\n  }\n";
+  o << "  double tot;\n  __device__ __forceinline__ double& total_ref(const SsaRunParams& p) {\n    tot = propensities(p);\n    return tot;\n  }\n";
   o << "  __device__ __forceinline__ double propensities(const SsaRunParams& p) {\n";
   o << "    double c = 0.0, pi;\n";
   if (low.groups.empty()) o << "    (void)pi; (void)p;\n    ck[0] = c;\n";
@@ -422,7 +424,7 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   }
   for (int s = 0; s < S; ++s)
     if (need_d[s]) o << "    const double d" << s << " = rb_bias_f64(x[" << s << "], p);\n";
-  if (R == 0) o << "    return 0.0;\n";
+  if (R == 0) o << "    c[0] = 0.0;\n    return 0.0;\n";
   for (int r = 0; r < R; ++r) {
     const RbReaction& rx = net.rx[r];
     std::string a;
@@ -464,6 +466,10 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   for (int r = 0; r < R; ++r) o << "    asm volatile(\"\" : \"+d\"(c[" << r << "]));\n";
   if (R > 0) o << "    return c[" << R - 1 << "];\n";
   o << "  }\n";
+
+  // the total as the last cumulative rate itself (not a copy: the sparse pass overwrites it on a cold path)
+  o << "  __device__ __forceinline__ double& total_ref(const SsaRunParams& p) {\n    propensities(p);\n    return c["
+    << (R ? R - 1 : 0) << "];\n  }\n";
 
   // select + update
   o << "  __device__ __forceinline__ int select(const SsaRunParams&, double chosen) const {\n";

@@ -115,6 +115,11 @@ struct RbTableNet {
   }
 
   // make_cumrates (src/gillespie.rs:357-364); only the total is kept, select() re-walks the sum.
+  double tot;
+  __device__ __forceinline__ double& total_ref(const SsaRunParams& p) {
+    tot = propensities(p);
+    return tot;
+  }
   __device__ __forceinline__ double propensities(const SsaRunParams& p) const {
     const int R = n_reactions;
     const uint4* rec = reinterpret_cast<const uint4*>(p.gtab);
