@@ -2,6 +2,7 @@
 #include "pdm.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ssa_params.h"
@@ -76,7 +77,9 @@ int rb_pdm_lower(const rebop_network& net, RbPdmLowered* out, std::string* why) 
     return no("at most " + std::to_string(RB_MAX_K) + " derived constants (owner species + distinct reactant pairs)");
   const unsigned ng = (unsigned)out->groups.size();
   out->group_size = 1;
-  while ((ng + out->group_size - 1) / out->group_size > RB_PDM_MAX_CHECKPOINTS) ++out->group_size;
+  unsigned max_ck = RB_PDM_MAX_CHECKPOINTS;
+  if (const char* env = std::getenv("REBOP_B200_PDM_CK")) max_ck = (unsigned)std::max(1, std::atoi(env));  // development knob
+  while ((ng + out->group_size - 1) / out->group_size > max_ck) ++out->group_size;
   out->n_checkpoints = ng ? (ng + out->group_size - 1) / out->group_size : 1;
 
   // device image
