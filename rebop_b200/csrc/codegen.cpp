@@ -538,6 +538,10 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   o << "  static __device__ __forceinline__ int none() { return " << (macro ? 0 : R * (prescale ? 4 * dwp : 1)) << "; }\n";
   // samples: saved species in ascending index order, selected by a launch-time bit mask
   o << "  __device__ __forceinline__ void record(const SsaRunParams& p, int* dst, rb_u32 stride) const {\n";
+  // every species saved (the usual case): rows at compile-time offsets, no tests of the mask
+  o << "    if (p.n_save == " << S << "u) {\n";
+  for (int s = 0; s < S; ++s) o << "      dst[(size_t)" << s << " * stride] = rb_bias_int(x[" << s << "]);\n";
+  o << "      return;\n    }\n";
   o << "    rb_u32 row = 0;\n";
   for (int s = 0; s < S; ++s) {
     o << "    if (p.save_mask[" << s / 64 << "] & " << (1ull << (s % 64)) << "ull) { dst[(size_t)row * stride] = rb_bias_int(x[" << s

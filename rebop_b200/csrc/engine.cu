@@ -784,13 +784,16 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
   RB_CUDA(cudaMemsetAsync(b->d_counters + 3, 0, sizeof(rb_u64), b->stream));  // work counter of this launch
 
   // grid times, exactly as the binding computes them: tmax * i as f64 / nb_steps as f64 (src/pyo3_gillespie.rs:201)
-  std::vector<double> grid_t;
+  // (nb_steps = 0, Gillespie::advance_until: the table holds the single target, so that the kernels read their grid
+  // times one way only)
+  std::vector<double> grid_t(n_points, tmax);
   if (nb_steps > 0) {
-    grid_t.resize(n_points);
     for (unsigned i = 0; i < n_points; ++i) {
       volatile double prod = tmax * (double)(step_first + i);  // volatile: one rounding per operation, no contraction
       grid_t[i] = prod / (double)nb_steps;
     }
+  }
+  {
     int st = ensure_capacity(&b->d_grid_t, &b->grid_t_capacity, (size_t)n_points);
     if (st) return st;
     RB_CUDA(cudaMemcpyAsync(b->d_grid_t, grid_t.data(), n_points * sizeof(double), cudaMemcpyHostToDevice, b->stream));
