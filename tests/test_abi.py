@@ -290,3 +290,24 @@ def test_generated_kernels_fit_their_register_budget_without_spills(ffi, tmp_pat
     for fn, regs, stack in found:
         assert int(regs) <= max_regs, (fn, regs)
         assert int(stack) == 0, (fn, "spills", stack)
+
+
+@pytest.mark.parametrize("name,arith,kernel,budget", [
+    ("vilar", 1, "rb_ssa_jit_dyn", 170),    # 164 at the end of round 2 (185 at its start): the headline kernel is issue-bound
+    ("dimers", 1, "rb_ssa_jit_dyn", 112),   # 107
+    ("sir", 0, "rb_ssa_jit_dns", 110),      # 103
+])
+def test_pass_stays_within_its_instruction_budget(ffi, tmp_path, name, arith, kernel, budget):
+    """The ensemble kernels are bound by issue slots, so the number of SASS instructions on the
+    hot path of the pass is the figure to watch: scripts/sass_path.py counts it from the NVRTC cubin, no GPU needed."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    net = models.build_network(models.MODELS[name](), arith)
+    cubin = tmp_path / "k.cubin"
+    cubin.write_bytes(net.jit_cubin())
+    out = subprocess.check_output([sys.executable, os.path.join(root, "scripts", "sass_path.py"), str(cubin), kernel], text=True)
+    m = re.search(r"hot path (\d+) instructions", out)
+    assert m, out
+    assert 60 <= int(m.group(1)) <= budget, out
