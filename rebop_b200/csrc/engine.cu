@@ -552,7 +552,7 @@ static unsigned pow2_floor(unsigned v) {
 static unsigned choose_ring_depth(const rebop_batch* b, unsigned block, unsigned net_words, unsigned n_save,
                                   unsigned n_points, unsigned ctas_per_sm) {
   if (n_save == 0) return 1;
-  const size_t fixed = RB_STATIC_SMEM_BYTES + 1024 + 4u * net_words;  // + per-CTA reservation
+  const size_t fixed = RB_STATIC_SMEM_BYTES + 8u * block + 1024 + 4u * net_words;  // + the loop's grid-time slots + per-CTA reservation
   const size_t per_depth = (size_t)(block / 32u) * n_save * 32u * 4u;
   const size_t budget = (size_t)b->max_smem_optin / (ctas_per_sm ? ctas_per_sm : 1);
   if (budget < fixed + per_depth) return 0;  // no room for a ring: samples go straight to global memory
@@ -862,7 +862,7 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     }
     p.ring_depth = claim ? 0u : choose_ring_depth(b, block, jit.net_words + jit.static_smem / 4u, p.n_save, n_points, ctas);
     const size_t smem = RB_SSA_SMEM_BYTES(jit.net_words, block, p.ring_depth, p.n_save);
-    if (smem + RB_STATIC_SMEM_BYTES + jit.static_smem > (size_t)b->max_smem_optin)
+    if (smem + RB_STATIC_SMEM_BYTES + 8u * block + jit.static_smem > (size_t)b->max_smem_optin)  // 8 * block: the loop's grid-time slots
       return rb_fail(REBOP_ERR_LIMIT, "specialised kernel: species state does not fit in shared memory");
     unsigned grid = (unsigned)((b->n + block - 1) / block);
     if (claim) {
@@ -889,7 +889,7 @@ static int launch(rebop_batch* b, double tmax, uint32_t nb_steps, uint32_t step_
     const unsigned net_words = S * block;
     p.ring_depth = claim ? 0u : choose_ring_depth(b, block, net_words, p.n_save, n_points, 8);
     const size_t smem = RB_SSA_SMEM_BYTES(net_words, block, p.ring_depth, p.n_save);
-    if (smem + RB_STATIC_SMEM_BYTES > (size_t)b->max_smem_optin)
+    if (smem + RB_STATIC_SMEM_BYTES + 8u * block > (size_t)b->max_smem_optin)
       return rb_fail(REBOP_ERR_LIMIT, "table-driven kernel: species state and sample ring do not fit in shared memory");
     unsigned grid = (unsigned)((b->n + block - 1) / block);
     if (claim) {
