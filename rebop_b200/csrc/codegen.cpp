@@ -392,8 +392,8 @@ std::string rb_codegen_source(const rebop_network& net, const std::string& kerne
   o << "struct RbGenNet {\n";
   o << "  static constexpr int BLOCK = " << block << ";\n";
   // define_system! arithmetic: a NaN `chosen` matches no reaction (first-match chains), see rb_ssa_loop
-  o << "#ifdef RB_X_NO_NANPICK\n  static constexpr bool NAN_PICKS_NONE = false;\n#else\n";
-  o << "  static constexpr bool NAN_PICKS_NONE = " << (macro ? "true" : "false") << ";\n#endif\n";
+  // (A/B against the NaN-waiting-time form: profiles/r2ad_sweep.log)
+  o << "  static constexpr bool NAN_PICKS_NONE = " << (macro ? "true" : "false") << ";\n";
   o << "  rb_state x[" << (S ? S : 1) << "];  // biased-double form, see ssa_kernel.cuh\n";
   o << "  double c[" << (R ? R : 1) << "];\n";
   o << "  static __device__ __forceinline__ int smem_words(const SsaRunParams&) { return 0; }\n";
